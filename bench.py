@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: path-steps/s of the fused Monte Carlo kernels on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gbm|merton] [--paths P] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: simulate `paths` paths per GPU for
+`num_steps` time steps, apply the payoff and reduce (sum, sum^2).  Default workload = BASELINE.json configs[1]
+(GBM 1-D European call, Euler-Maruyama, 1e9 paths x 252 steps, r=.02 sigma=.3 S0=K=1 T=3); `--workload merton`
+runs the Merton 1-D jump-adapted config the north-star target is quoted on (1e9 paths x 100 steps per GPU).
+Weak scaling: every rank simulates `paths` paths of a disjoint global path-id range; the only exchange is one
+all-reduce of 8 fp64 moments.  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the reference's own CPU algorithm (oracle/torch_port.py: eager PyTorch ops in a Python
+loop, pinned bit-for-bit to the unmodified reference) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# canonical algorithmic work per nominal path-step, in FP32/ALU/XU lane-operations (SURVEY.md section 8d,
+# restated in DESIGN.md): one N(0,1) = 21 ops; GBM Euler step 2 ops; Merton jump-adapted iteration 39 ops x 1.03.
+OPS_PER_PATH_STEP = {"gbm": 23.0, "merton": 40.0}
+WORKLOADS = {
+    "gbm": dict(name="gbm_1d_eurocall_euler_1e9x252", num_steps=252, paths=10 ** 9, cpu_paths=10 ** 5),
+    "merton": dict(name="merton_1d_eurocall_jump_adapted_euler_1e9x100", num_steps=100, paths=10 ** 9,
+                   cpu_paths=10 ** 5),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="gbm", choices=sorted(WORKLOADS))
+    ap.add_argument("--paths", type=float, default=None, help="paths per GPU per step (default: the config's 1e9)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def build_problem(sm, workload, device):
+    import torch
+    if workload == "gbm":
+        p = sm.BlackScholesEuroCall.default_params(252, device)
+        return p.solver, p.payoff, p.discounter, "terminal"
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    return (sm.JumpEulerSolver(sde, 3, 100, device=device), sm.EuroCall(1.0), sm.ConstantShortRate(0.02), "adapted")
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons of one GPU with nvidia-smi while the timed region runs"""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm_mhz, max_mhz, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm_mhz.append(float(s[0]))
+                max_mhz = max(max_mhz, float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm_mhz) if sm_mhz else None, "sm_max_mhz": max_mhz or None,
+                "reasons": sorted(reasons), "samples": len(sm_mhz)}
+
+
+def cpu_reference(workload, steps, warmup, sample_paths=None):
+    """the reference's CPU algorithm (torch port) on a bounded sample; returns (path-steps/s, info)"""
+    import torch
+    import sde_mc_b200 as sm
+    from oracle import torch_port as tp
+    w = WORKLOADS[workload]
+    n = int(sample_paths or w["cpu_paths"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    if workload == "gbm":
+        spec = sm.Gbm(0.02, 0.3, torch.tensor([1.]), 1).kernel_spec()
+        run = lambda: tp.mc_simple_batched(spec, 3, 252, n, n, tp.payoff_call_on("euro_call", 1.0), 0.02, False, "terminal")
+    else:
+        spec = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1).kernel_spec()
+        run = lambda: tp.mc_simple_batched(spec, 3, 100, n, n, tp.payoff_call_on("euro_call", 1.0), 0.02, True, "adapted")
+    torch.manual_seed(1)
+    for _ in range(warmup):
+        run()
+    times, est = [], None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        est = run()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = n * w["num_steps"] * steps / total
+    info = {"value": value, "unit": "path-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d paths x %d steps per step, %d timed steps, torch %s eager CPU (oracle/torch_port.py)" %
+                      (n, w["num_steps"], steps, torch.__version__),
+            "estimate": est[0], "stderr": est[1]}
+    return value, total / steps, info
+
+
+def main():
+    args = parse()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        k, wu = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+        value, sec, info = cpu_reference(args.workload, k, wu)
+        print(json.dumps({
+            "impl": "reference", "metric": "path_steps_per_sec", "value": value, "unit": "path-steps/s",
+            "n_gpus": args.gpus, "steps": k, "warmup": wu, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "sample": info["sample"]}, "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import sde_mc_b200 as sm
+    from sde_mc_b200 import _engine as E
+    from sde_mc_b200 import _lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    paths = int(args.paths or w["paths"])
+    solver, payoff, discounter, payoff_time = build_problem(sm, args.workload, dev)
+    index_mode = L.INDEX_ADAPTED if payoff_time == "adapted" else L.INDEX_TERMINAL
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident leg: inputs (a parameter struct + Philox key) are already on the device side ----
+    def device_step():
+        # every rank: `paths` paths of its own global path-id range (weak scaling), then the 64-byte all-reduce
+        return E.run_moments(solver, payoff, discounter, paths * world, index_mode)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    stream = torch.cuda.current_stream(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    mom = None
+    for _ in range(args.steps):
+        mom = device_step()
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    result = mom.read()
+
+    # ---- end-to-end leg: the public API call a user makes, host struct in -> python floats out ----
+    barrier()
+    t0 = time.perf_counter()
+    stats = None
+    for _ in range(args.steps):
+        stats = sm.mc_simple(paths * world, solver, payoff, discounter, bs=10 ** 6, payoff_time=payoff_time)
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if rank == 0:
+        time.sleep(0.2)
+        sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        total_path_steps = float(paths) * world * w["num_steps"] * args.steps
+        value = total_path_steps / (dev_ms * 1e-3)
+        e2e = total_path_steps / (e2e_ms * 1e-3)
+        clocks = sampler.summary()
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965.0
+        peak = sm_count * 128 * mhz * 1e6 / 1e12                      # Tlane-op/s at the clock measured under load
+        achieved = OPS_PER_PATH_STEP[args.workload] * (value / world) / 1e12
+        n_total = paths * world
+        import ctypes
+        h2d_bytes = ctypes.sizeof(L.SdemcSde) + ctypes.sizeof(L.SdemcPayoff) + ctypes.sizeof(L.SdemcRange) + 40 * 2
+        mean, se = E.mean_and_stderr(result["sum"], result["sumsq"], n_total)
+        out = {
+            "metric": "path_steps_per_sec", "value": value, "unit": "path-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "paths_per_gpu_per_step": paths, "num_steps": w["num_steps"],
+                       "payoff_time": payoff_time, "moments": "fp64", "rng": "philox4x32-10 in registers",
+                       "l2": "kernel reads no global inputs (parameters in constant bank); nothing to flush",
+                       "parallelism": "paths sharded over %d GPU(s), one 64-byte all-reduce per step" % world},
+            "e2e": {"value": e2e, "unit": "path-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "call": "sde_mc_b200.mc_simple(paths, solver, payoff, discounter, bs=1e6)"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak, "unit": "Tlaneop/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "ops_per_path_step": OPS_PER_PATH_STEP[args.workload],
+                         "peak_def": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock sampled during the run)"
+                                     % (sm_count, mhz),
+                         "executed_iterations_per_path": result["iters"] / result["n"]},
+            "estimate": {"mean": mean, "stderr": se, "n": n_total,
+                         "closed_form": 0.22943206 if args.workload == "gbm" else 0.26298121},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            _, _, info = cpu_reference(args.workload, 2, 1)
+            out["cpu_baseline"] = info
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

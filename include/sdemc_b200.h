@@ -1,0 +1,202 @@
+/*
+ * sdemc_b200.h -- C-ABI of libsdemc_b200.so, the B200 (sm_100a) Monte Carlo engine behind
+ * the sde_mc Python API.
+ *
+ * The reference (piers-hinds/sde_mc) has no FFI of its own: its boundary is the Python API
+ * (SdeSolver.solve / multilevel_solve, mc_simple, mc_multilevel, mc_apply_cvs ...).  These entry
+ * points are what a ctypes binding on the reference side would call in place of the Python step
+ * loops; each one cites the reference code it replaces.  See INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *   - plain C, POD structs, no exceptions; every function returns 0 or a negative sdemc_status
+ *   - all `d_*` pointers are DEVICE pointers owned by the caller (e.g. torch tensors)
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); calls are asynchronous w.r.t. it
+ *   - the library keeps no mutable global state; the caller provides scratch (`d_workspace`)
+ *   - all path arithmetic is fp32 like the reference (torch default dtype); the moment
+ *     accumulators are fp64; the MLMC pair entry point also has an fp64-state variant
+ */
+#ifndef SDEMC_B200_H
+#define SDEMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDEMC_ABI_VERSION 1
+#define SDEMC_MAX_DIM 4
+#define SDEMC_MAX_LEVELS 16
+
+typedef enum {
+  SDEMC_OK = 0,
+  SDEMC_ERR_BAD_ARG = -1,      /* NULL pointer, negative size, inconsistent struct */
+  SDEMC_ERR_UNSUPPORTED = -2,  /* (model, scheme, dim, m) combination without a kernel */
+  SDEMC_ERR_CUDA = -3,         /* CUDA runtime error; text via sdemc_last_cuda_error() */
+  SDEMC_ERR_NO_DEVICE = -4,    /* no sm_100 device */
+  SDEMC_ERR_WORKSPACE = -5     /* workspace too small */
+} sdemc_status;
+
+/* Coefficient families.  Each reference Sde class maps to one (sde.py / levy.py):
+ *   GEOMETRIC : drift a_i x_i, diffusion b1_i x_i (+ b2_i x_i), jump c_i x_i J
+ *               Gbm sde.py:179-207, DoubleGbm :222-255, Merton :335-375,
+ *               LevySde(ExpExampleLevy) levy.py:65-96,132-160
+ *   ARITHMETIC: drift a_i, diffusion b1_i (+ b2_i), jump c_i J   (log-price models)
+ *               LogGbm sde.py:210-219, LevySde(ExampleLevy) levy.py:99-129, LevySde(Levy2d) :163-192
+ *   HESTON    : sde.py:258-279 with the drift-implicit square-root scheme schemes.py:16-22
+ */
+typedef enum { SDEMC_FAMILY_GEOMETRIC = 0, SDEMC_FAMILY_ARITHMETIC = 1, SDEMC_FAMILY_HESTON = 2 } sdemc_family;
+
+/* schemes.py:5-22.  MILSTEIN is an extension (absent from the reference, parity unpinned). */
+typedef enum { SDEMC_SCHEME_EULER = 0, SDEMC_SCHEME_HESTON = 1, SDEMC_SCHEME_MILSTEIN = 2 } sdemc_scheme;
+
+/* Jump mark distributions: LogNormalJumpsSde.sample_jumps sde.py:325-326, LevySde.sample_jumps levy.py:85-87 */
+typedef enum { SDEMC_MARKS_NONE = 0, SDEMC_MARKS_LOGNORMAL = 1, SDEMC_MARKS_ICDF = 2 } sdemc_marks;
+
+/* How the kernels draw compound-Poisson jumps from Philox (no reference counterpart: the reference pre-samples
+ * max_jumps exponential gaps per path, solvers.py:143-144,178).  QUEUE: per-thread shared-memory queue of
+ * pre-drawn (time, mark) pairs -- for sparse jumps.  INLINE: one candidate per iteration in registers -- for
+ * dense jumps.  The two strategies consume different Philox counters, so estimates agree statistically only. */
+typedef enum { SDEMC_JUMPS_AUTO = 0, SDEMC_JUMPS_QUEUE = 1, SDEMC_JUMPS_INLINE = 2 } sdemc_jump_strategy;
+
+/* options.py:179-321 */
+typedef enum {
+  SDEMC_PAYOFF_EURO_CALL = 0, SDEMC_PAYOFF_EURO_PUT = 1, SDEMC_PAYOFF_BINARY_AON = 2,
+  SDEMC_PAYOFF_BASKET_ARITH = 3, SDEMC_PAYOFF_BASKET_GEOM = 4, SDEMC_PAYOFF_RAINBOW = 5,
+  SDEMC_PAYOFF_DIGITAL = 6, SDEMC_PAYOFF_ASIAN_CALL = 7, SDEMC_PAYOFF_HESTON_RAINBOW = 8,
+  SDEMC_PAYOFF_BEST_OF = 9
+} sdemc_payoff_kind;
+
+/* mc.py:84-91 -- which stored state the payoff is applied to */
+typedef enum { SDEMC_INDEX_TERMINAL = 0 /* array index num_steps */, SDEMC_INDEX_ADAPTED = 1 /* last state */ } sdemc_index_mode;
+
+/* The SDE + discretisation, extracted from (Sde, SdeSolver) objects. Replaces the attribute reads in
+ * solvers.py:10-37,131-134 and the coefficient callbacks sde.py:63-152. */
+typedef struct {
+  int32_t family;       /* sdemc_family */
+  int32_t scheme;       /* sdemc_scheme */
+  int32_t dim;          /* state dimension, 1..SDEMC_MAX_DIM (Sde.dim) */
+  int32_t m;            /* Brownian drivers per component: 1 = 'diag', 2 = 'indep' (brown_dim/dim) */
+  int32_t marks;        /* sdemc_marks; NONE => pure diffusion */
+  int32_t num_steps;    /* SdeSolver.num_steps */
+  int32_t max_jumps;    /* JumpDiffusionSolver.max_jumps solvers.py:133 (sizes the storage arrays) */
+  int32_t exact_jumps;  /* solvers.py:214-217 */
+  int32_t asian;        /* 1: AsianWrapper sde.py:378-406 -- component dim-1 integrates component 0 */
+  int32_t jump_strategy; /* sdemc_jump_strategy: how Philox jump draws are organised (AUTO picks by rate*T/num_steps) */
+  float T;              /* SdeSolver.time_interval */
+  float x0[SDEMC_MAX_DIM];
+  float chol[SDEMC_MAX_DIM * SDEMC_MAX_DIM]; /* lower Cholesky of corr_matrix, row-major, stride SDEMC_MAX_DIM */
+  float a[SDEMC_MAX_DIM];   /* drift coefficients        */
+  float b1[SDEMC_MAX_DIM];  /* first-driver diffusion    */
+  float b2[SDEMC_MAX_DIM];  /* second-driver diffusion   */
+  float c[SDEMC_MAX_DIM];   /* jump coefficients         */
+  float rate;               /* sde.jump_rate().sum()     */
+  /* mark parameters: LOGNORMAL {alpha, gamma};  ICDF {cm, cp, mu, alpha, eps, lda, y1, y2, y3} levy.py:10-30 */
+  float mark_p[12];
+  /* Heston {r, kappa, theta, xi} sde.py:258-279 */
+  float heston[4];
+} sdemc_sde;
+
+/* Option + discounter: options.py:156-176 (transform), :179-321 (payoffs), :324-337 (ConstantShortRate) */
+typedef struct {
+  int32_t kind;        /* sdemc_payoff_kind */
+  int32_t log;         /* Option.log */
+  int32_t index_mode;  /* sdemc_index_mode */
+  float strike;
+  float transform_discount; /* Option.discount (multiplies the spot before the payoff) */
+  float aux;           /* AsianCall.time_interval */
+  float df;            /* discounter(T): factor multiplying the payoff, mc.py:93 */
+} sdemc_payoff;
+
+/* Which paths, and where their noise comes from.  Philox4x32-10 keyed by `seed`, countered by the GLOBAL
+ * path id, so results do not depend on grid shape or on how a range is split over GPUs. */
+typedef struct {
+  uint64_t seed;
+  uint64_t path_lo;    /* first global path id of this call */
+  uint64_t n_paths;    /* number of paths in this call */
+} sdemc_range;
+
+/* Injected noise for the deterministic-parity mode (replaces the three overridable sampling methods
+ * sample_corr_normals solvers.py:51-56, sample_jump_times :143-144, sample_one_jump :146-148).
+ * All arrays are row-major, one row per path. K = number of loop iterations available. */
+typedef struct {
+  const float* d_z;          /* (n, K, dim, m') unit normals; m' = m for the diffusion solver, 1 for the jump solver */
+  const float* d_zc;         /* (n, K) common unit normal of the 2nd driver (jump solver, m == 2), else NULL */
+  const float* d_jump_times; /* (n, max_jumps) cumulative jump times, else NULL */
+  const float* d_marks;      /* (n, K) raw mark draw per iteration: N(0,1) for LOGNORMAL, U[0,1) for ICDF */
+  int32_t K;
+} sdemc_inject;
+
+/* fp64 running moments; layout of the device array handed to the kernels (8 doubles). */
+typedef struct {
+  double sum;       /* sum of discounted payoffs (or MLMC corrections, or CV-corrected payoffs) */
+  double sumsq;
+  double sum_c;     /* terminal control  D(T) x_T[0] - x_0[0]  (mc.py:337) */
+  double sumsq_c;
+  double sum_pc;
+  double n;         /* paths accumulated */
+  double iters;     /* executed loop iterations over all paths */
+  double reserved;
+} sdemc_moments;
+
+/* Optional trajectory outputs, layouts exactly as the reference allocates them (solvers.py:64-66,150-162).
+ * S = num_steps for the diffusion solver, num_steps + max_jumps for the jump solver.  NULL = skip. */
+typedef struct {
+  float* d_paths;       /* (n, S+1, dim) */
+  float* d_left;        /* (n, S+1, dim)  state before the jump            (jump solver) */
+  float* d_times;       /* (n, S+1)       time after each iteration        (jump solver) */
+  float* d_jumps;       /* (n, S+1, dim)  applied jump mark                (jump solver) */
+  float* d_normals;     /* (n, S, dim[, m]) Brownian increments dW actually used */
+  float* d_payoffs;     /* (n)            discounted payoff per path */
+  int32_t* d_iters;     /* (n)            executed iterations per path */
+  int32_t* d_total_steps; /* scalar: max over paths of executed iterations (atomicMax; caller zeroes it) */
+} sdemc_paths_out;
+
+/* Control-variate networks for the fused CV kernel: the BN-free Mlp of nets.py:39-93,
+ * Linear(d+1,H) ReLU Linear(H,H) ReLU Linear(H,H) ReLU Linear(H,out). Weights are torch Linear
+ * layouts (out_features, in_features) row-major fp32, device pointers. */
+typedef struct {
+  const float* d_w[4];
+  const float* d_b[4];
+  int32_t in_dim, hidden, out_dim, n_hidden_layers; /* n_hidden_layers == 3 */
+} sdemc_mlp;
+
+int sdemc_version(void);
+const char* sdemc_strerror(int rc);
+const char* sdemc_last_cuda_error(void);
+/* SM count, SM clock (kHz) and global memory of `device`; any pointer may be NULL. */
+int sdemc_device_info(int device, int* sm_count, int* clock_khz, uint64_t* mem_bytes);
+/* Bytes of device scratch every entry point needs (per concurrent call). */
+uint64_t sdemc_workspace_bytes(void);
+
+/* E1/H3/H10 fused: time-stepping + payoff + (sum, sumsq, ...) reduction; nothing per-path touches HBM.
+ * Replaces the bodies of mc_simple mc.py:101-123, mc_terminal_cv mc.py:352-375 and the solve() they call.
+ * d_moments (sdemc_moments) is ACCUMULATED into (caller zeroes it once per estimator). */
+int sdemc_mc_moments(const sdemc_sde* sde, const sdemc_payoff* payoff, const sdemc_range* range,
+                     sdemc_moments* d_moments, void* d_workspace, void* stream);
+
+/* H3/H10 with storage: the solve() contract (solvers.py:68-88,164-226).  Noise is Philox (inject == NULL)
+ * or injected (deterministic parity mode).  Any subset of outputs may be requested. */
+int sdemc_solve_paths(const sdemc_sde* sde, const sdemc_payoff* payoff /* may be NULL */, const sdemc_range* range,
+                      const sdemc_inject* inject /* may be NULL */, const sdemc_paths_out* out,
+                      void* d_workspace, void* stream);
+
+/* H11/E4 fused: coupled fine/coarse jump-adapted (or uniform-grid) pair sharing increments and jumps,
+ * accumulating D(T) (P(fine) - P(coarse)).  coarse == 0 runs the single level `fine` (mlmc.py:44-53).
+ * use_fp64 != 0 keeps the path state in fp64 (the reference's jump MLMC only runs in fp64).
+ * With inject != NULL and d_pair_out != NULL writes (n, 2, dim) terminal (fine, coarse) states instead. */
+int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse, int32_t use_fp64,
+                    const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments,
+                    void* d_pair_out, void* d_workspace, void* stream);
+
+/* E5/E6/E7 fused: simulate + evaluate the control-variate MLPs f, g along each path on tensor cores and
+ * accumulate gamma = payoff + sum f dW D + sum g D J - sum rate E[J] g D h  (varred.py:98-131).
+ * g may be NULL for pure diffusions (varred.py:75-95). jump_mean = sde.jump_mean(). */
+int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rate, float jump_mean,
+                const sdemc_mlp* f, const sdemc_mlp* g, const sdemc_range* range, const sdemc_inject* inject,
+                sdemc_moments* d_moments, float* d_gamma_out /* (n) or NULL */, void* d_workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDEMC_B200_H */

@@ -1,0 +1,105 @@
+// diffusion.cuh -- fused uniform-grid kernels: DiffusionSolver.solve (solvers.py:68-88) + payoff + moments.
+#pragma once
+#include "engine.cuh"
+
+namespace sdemc {
+
+// One thread per path, grid-stride over the call's path range.
+//   INJECT : unit normals come from DevInject.z (deterministic parity mode) instead of Philox
+//   STORE  : write the solve() outputs (paths, normals, payoffs); otherwise accumulate moments only
+template <class C, bool HESTON, bool INJECT, bool STORE>
+__global__ void __launch_bounds__(256) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+                                                        const PhiloxKeys keys, const DevInject inj, const DevOut out,
+                                                        double* __restrict__ d_moments, void* __restrict__ d_ws) {
+  constexpr int DIM = C::DIM, M = C::M, BASE = C::BASE;
+  constexpr int NZ = BASE * M;            // normals consumed per step
+  constexpr int NZP = pad_pow2(NZ);       // padded to a divisor / multiple of the 4-word Philox block
+  constexpr int SPB = NZP <= 4 ? 4 / NZP : 1;  // steps served by one group of blocks
+  constexpr int BPS = NZP <= 4 ? 1 : NZP / 4;  // Philox blocks per group
+  const int S = s.num_steps;
+
+  Accum acc;
+  acc.zero();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
+    const uint64_t gp = rg.path_lo + i;
+    const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
+    float x[kMaxDim];
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) x[d] = d < DIM ? s.x0[d] : 0.0f;
+    if (STORE && out.paths) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) out.paths[(i * (uint64_t)(S + 1)) * DIM + d] = x[d];
+    }
+
+    for (int b = 0; b * SPB < S; ++b) {
+      float nrm[SPB * NZP];
+      float extra[SPB];  // injected normal of the asian integral component (recorded, never used)
+      if (!INJECT) {
+#pragma unroll
+        for (int r = 0; r < BPS; ++r) {
+          uint32_t o[4];
+          philox4x32_10((uint32_t)(b * BPS + r), STREAM_DIFFUSION, plo, phi, keys, o);
+          box_muller(o[0], o[1], nrm[4 * r + 0], nrm[4 * r + 1]);
+          box_muller(o[2], o[3], nrm[4 * r + 2], nrm[4 * r + 3]);
+        }
+#pragma unroll
+        for (int sp = 0; sp < SPB; ++sp) extra[sp] = 0.0f;
+      } else {
+#pragma unroll
+        for (int sp = 0; sp < SPB; ++sp) {
+          const int step = b * SPB + sp;
+          extra[sp] = 0.0f;
+          if (step < S) {
+            const float* zp = inj.z + (i * (uint64_t)S + step) * (DIM * M);
+#pragma unroll
+            for (int q = 0; q < NZ; ++q) nrm[sp * NZP + q] = zp[q];
+            if (C::ASIAN) extra[sp] = zp[BASE * M];
+          }
+        }
+      }
+#pragma unroll
+      for (int sp = 0; sp < SPB; ++sp) {
+        const int step = b * SPB + sp;
+        if (step < S) {
+          float z1[kMaxDim], z2[kMaxDim], w1[kMaxDim], w2[kMaxDim];
+#pragma unroll
+          for (int k = 0; k < BASE; ++k) {
+            z1[k] = nrm[sp * NZP + k * M];
+            z2[k] = M == 2 ? nrm[sp * NZP + k * M + 1] : 0.0f;
+          }
+          correlate<C>(s, z1, w1);
+          if (M == 2) correlate<C>(s, z2, w2);  // DiffusionSolver: every driver is a correlated dim-vector (:79-81)
+          if (HESTON) heston_step_uniform(s, x, w1);
+          else euler_step_uniform<C>(s, x, w1, w2);
+          if (STORE) {
+            if (out.paths) {
+#pragma unroll
+              for (int d = 0; d < DIM; ++d) out.paths[(i * (uint64_t)(S + 1) + step + 1) * DIM + d] = x[d];
+            }
+            if (out.normals) {
+              float* np = out.normals + (i * (uint64_t)S + step) * (DIM * M);
+#pragma unroll
+              for (int d = 0; d < BASE; ++d) {
+                np[d * M] = w1[d] * s.sqrt_h0;
+                if (M == 2) np[d * M + 1] = w2[d] * s.sqrt_h0;
+              }
+              if (C::ASIAN) np[BASE * M] = extra[sp] * s.sqrt_h0;
+            }
+          }
+        }
+      }
+    }
+
+    const float pay = eval_payoff<DIM>(po, x);
+    if (STORE) {
+      if (out.payoffs) out.payoffs[i] = pay;
+      if (out.iters) out.iters[i] = S;
+    } else {
+      acc.add(pay, po.df * x[0] - s.x0[0], S);  // terminal control  D(T) x_T[0] - x_0[0]  mc.py:337
+    }
+  }
+  if (!STORE) block_reduce_and_publish(acc, d_moments, d_ws);
+}
+
+}  // namespace sdemc

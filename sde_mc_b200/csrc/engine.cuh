@@ -1,0 +1,313 @@
+// engine.cuh -- device-side building blocks of the fused path kernels.
+//
+// One thread owns one path: state, time, step size, next jump and RNG counters live in registers for all
+// time steps (reference: the Python loops DiffusionSolver.solve solvers.py:68-88 and
+// JumpDiffusionSolver.solve solvers.py:164-226, which issue 20-244 ATen ops per step on (bs, dim) tensors).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/sdemc_b200.h"
+#include "philox.cuh"
+
+namespace sdemc {
+
+constexpr int kMaxDim = SDEMC_MAX_DIM;
+
+// ------------------------------------------------------------------------------------------------------------
+// Device copies of the problem (passed by value as kernel parameters -> constant bank / uniform registers)
+// ------------------------------------------------------------------------------------------------------------
+struct DevSde {
+  int num_steps, max_jumps, exact_jumps;
+  float T, h0, sqrt_h0;
+  float x0[kMaxDim];
+  float chol[kMaxDim * kMaxDim];
+  float a[kMaxDim], b1[kMaxDim], b2[kMaxDim], c[kMaxDim];
+  // uniform-grid constants: geometric 1 + a h, arithmetic a h ; b * sqrt(h)
+  float ah[kMaxDim], b1s[kMaxDim], b2s[kMaxDim];
+  float rate, inv_rate;
+  // lognormal marks  J = 2^(z * g2 + a2) - 1
+  float ln_a2, ln_g2;
+  // icdf marks (levy.py:10-30), pre-combined constants
+  float ic_y1, ic_y2, ic_y3, ic_mulda_cm, ic_inv_mu_ln2, ic_alpha, ic_lda_cm, ic_inv_mu, ic_neg_inv_alpha,
+      ic_malpha_cp, ic_lda, ic_x3_off, ic_eps_ma, ic_mulda_cp, ic_tol;
+  // heston
+  float hes_r, hes_kappa, hes_xi, hes_kth, hes_halfxi2;
+};
+
+struct DevPayoff {
+  int kind, log, index_mode;
+  float strike, tdisc, aux, df;
+};
+
+struct DevRange {
+  uint64_t path_lo, n_paths;
+};
+
+struct DevInject {
+  const float* z;
+  const float* zc;
+  const float* jump_times;
+  const float* marks;
+  int K;
+};
+
+struct DevOut {
+  float* paths;
+  float* left;
+  float* times;
+  float* jumps;
+  float* normals;
+  float* payoffs;
+  int* iters;
+  int* total_steps;
+  int S;  // allocated iterations per path (rows are S+1 / S long)
+};
+
+// compile-time configuration of a kernel instance
+template <int FAMILY_, int DIM_, int M_, int MARKS_, bool ASIAN_>
+struct Cfg {
+  static constexpr int FAMILY = FAMILY_, DIM = DIM_, M = M_, MARKS = MARKS_;
+  static constexpr bool ASIAN = ASIAN_;
+  static constexpr int BASE = ASIAN_ ? DIM_ - 1 : DIM_;  // components driven by noise
+};
+
+constexpr int pad_pow2(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : 8; }
+
+// ------------------------------------------------------------------------------------------------------------
+// marks
+// ------------------------------------------------------------------------------------------------------------
+// InverseCdf.__call__ levy.py:19-30 with lg2/ex2 on the XU pipe; pow(x, p) = ex2(p * lg2(x)).
+__device__ __forceinline__ float icdf_mark(const DevSde& s, float u) {
+  const float y = u + s.ic_tol;  // levy.py:86
+  float r;
+  if (y <= s.ic_y1) {
+    r = fmaf(fast_lg2(s.ic_mulda_cm * y), s.ic_inv_mu_ln2, -1.0f);
+  } else if (y < s.ic_y2) {
+    r = -fast_ex2(s.ic_neg_inv_alpha * fast_lg2(fmaf(s.ic_alpha, fmaf(s.ic_lda_cm, y, -s.ic_inv_mu), 1.0f)));
+  } else if (y < s.ic_y3) {
+    r = fast_ex2(s.ic_neg_inv_alpha * fast_lg2(fmaf(s.ic_malpha_cp, fmaf(s.ic_lda, y, -s.ic_x3_off), s.ic_eps_ma)));
+  } else {
+    r = fmaf(-s.ic_inv_mu_ln2, fast_lg2(s.ic_mulda_cp * (1.0f - y)), 1.0f);
+  }
+  return r;
+}
+
+// raw draw -> jump mark.  LOGNORMAL: raw ~ N(0,1), sde.py:325-326.  ICDF: raw ~ U[0,1), levy.py:85-87.
+template <int MARKS>
+__device__ __forceinline__ float mark_from_raw(const DevSde& s, float raw) {
+  if (MARKS == SDEMC_MARKS_LOGNORMAL) return fast_ex2(fmaf(raw, s.ln_g2, s.ln_a2)) - 1.0f;
+  if (MARKS == SDEMC_MARKS_ICDF) return icdf_mark(s, raw);
+  return 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// schemes
+// ------------------------------------------------------------------------------------------------------------
+// w[j][i] = sum_k L[i][k] z[k][j]   (torch.matmul(lower_cholesky, normals) solvers.py:54), unit variance
+template <class C>
+__device__ __forceinline__ void correlate(const DevSde& s, const float (&z)[kMaxDim], float (&w)[kMaxDim]) {
+#pragma unroll
+  for (int i = 0; i < C::BASE; ++i) {
+    float acc = s.chol[i * kMaxDim] * z[0];
+#pragma unroll
+    for (int k = 1; k <= i; ++k) acc = fmaf(s.chol[i * kMaxDim + k], z[k], acc);
+    w[i] = acc;
+  }
+}
+
+// EulerScheme.step schemes.py:5-13 for a step (dt, sqrt(dt)) with unit-variance correlated normals w1 (per
+// component) and w2 (second driver).  Algebraically regrouped per family:
+//   geometric  x (1 + a dt + b1 sq w1 + b2 sq w2)      arithmetic  x + a dt + b1 sq w1 + b2 sq w2
+template <class C>
+__device__ __forceinline__ void euler_step(const DevSde& s, float (&x)[kMaxDim], float dt, float sq,
+                                           const float (&w1)[kMaxDim], const float (&w2)[kMaxDim]) {
+  const float x_first = x[0];
+#pragma unroll
+  for (int i = 0; i < C::BASE; ++i) {
+    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
+      float g = fmaf(s.a[i], dt, 1.0f);
+      g = fmaf(s.b1[i] * sq, w1[i], g);
+      if (C::M == 2) g = fmaf(s.b2[i] * sq, w2[i], g);
+      x[i] *= g;
+    } else {
+      float v = fmaf(s.a[i], dt, x[i]);
+      v = fmaf(s.b1[i] * sq, w1[i], v);
+      if (C::M == 2) v = fmaf(s.b2[i] * sq, w2[i], v);
+      x[i] = v;
+    }
+  }
+  if (C::ASIAN) x[C::DIM - 1] = fmaf(x_first, dt, x[C::DIM - 1]);  // AsianWrapper.drift sde.py:396-397
+}
+
+// same, on the uniform grid of DiffusionSolver (h, sqrt(h) folded into per-launch constants)
+template <class C>
+__device__ __forceinline__ void euler_step_uniform(const DevSde& s, float (&x)[kMaxDim], const float (&w1)[kMaxDim],
+                                                   const float (&w2)[kMaxDim]) {
+  const float x_first = x[0];
+#pragma unroll
+  for (int i = 0; i < C::BASE; ++i) {
+    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
+      float g = fmaf(s.b1s[i], w1[i], s.ah[i]);
+      if (C::M == 2) g = fmaf(s.b2s[i], w2[i], g);
+      x[i] *= g;
+    } else {
+      float v = fmaf(s.b1s[i], w1[i], x[i] + s.ah[i]);
+      if (C::M == 2) v = fmaf(s.b2s[i], w2[i], v);
+      x[i] = v;
+    }
+  }
+  if (C::ASIAN) x[C::DIM - 1] = fmaf(x_first, s.h0, x[C::DIM - 1]);
+}
+
+// HestonScheme.step schemes.py:16-22 + Heston.quadratic_parameters sde.py:275-279 + solve_quadratic
+// helpers.py:36-48.  w = correlated unit normals; increments are w * sqrt(h).
+__device__ __forceinline__ void heston_step_uniform(const DevSde& s, float (&x)[kMaxDim], const float (&w)[kMaxDim]) {
+  const float S = x[0], v = x[1], h = s.h0;
+  const float dw0 = w[0] * s.sqrt_h0, dw1 = w[1] * s.sqrt_h0;
+  x[0] = fmaf(sqrtf(v) * S, dw0, fmaf(s.hes_r * S, h, S));
+  const float qa = -1.0f - s.hes_kappa * h;
+  const float qb = s.hes_xi * dw1;
+  const float qc = fmaf(s.hes_kth, h, v) - s.hes_halfxi2 * h;
+  const float disc = sqrtf(fmaf(qb, qb, -4.0f * qa * qc));
+  const float inv = 1.0f / (2.0f * qa);
+  const float y = fmaxf((-qb + disc) * inv, (-qb - disc) * inv);
+  x[1] = y * y;
+}
+
+// sde.jumps(t, x_base, J): geometric c x J (sde.py:374-375, levy.py:154-155), arithmetic c J (levy.py:120-121)
+template <class C>
+__device__ __forceinline__ void add_jump(const DevSde& s, float (&x)[kMaxDim], const float (&xb)[kMaxDim], float J) {
+#pragma unroll
+  for (int i = 0; i < C::BASE; ++i) {
+    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) x[i] = fmaf(s.c[i] * xb[i], J, x[i]);
+    else x[i] = fmaf(s.c[i], J, x[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// payoff  (Option.__call__ options.py:167-176; payoffs options.py:196-321)
+// ------------------------------------------------------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ float eval_payoff(const DevPayoff& po, const float (&xin)[kMaxDim]) {
+  float x[kMaxDim];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) x[i] = po.tdisc * (po.log ? __expf(xin[i]) : xin[i]);
+  const float K = po.strike;
+  float sp, r;
+  switch (po.kind) {
+    case SDEMC_PAYOFF_EURO_CALL: r = x[0] > K ? x[0] - K : 0.0f; break;
+    case SDEMC_PAYOFF_EURO_PUT: r = x[0] < K ? K - x[0] : 0.0f; break;
+    case SDEMC_PAYOFF_BINARY_AON: r = x[0] >= K ? x[0] : 0.0f; break;
+    case SDEMC_PAYOFF_BASKET_ARITH:
+      sp = x[0];
+#pragma unroll
+      for (int i = 1; i < DIM; ++i) sp += x[i];
+      sp = sp / (float)DIM;
+      r = sp > K ? sp - K : 0.0f;
+      break;
+    case SDEMC_PAYOFF_BASKET_GEOM:
+      sp = __logf(x[0]);
+#pragma unroll
+      for (int i = 1; i < DIM; ++i) sp += __logf(x[i]);
+      sp = __expf(sp / (float)DIM);
+      r = sp > K ? sp - K : 0.0f;
+      break;
+    case SDEMC_PAYOFF_RAINBOW:
+      sp = x[0];
+#pragma unroll
+      for (int i = 1; i < DIM; ++i) sp = fmaxf(sp, x[i]);
+      r = sp > K ? sp - K : 0.0f;
+      break;
+    case SDEMC_PAYOFF_DIGITAL: r = x[0] > K ? 1.0f : 0.0f; break;
+    case SDEMC_PAYOFF_ASIAN_CALL:
+      sp = DIM > 1 ? x[DIM > 1 ? 1 : 0] / po.aux : 0.0f;
+      if (po.log) sp = __expf(sp);
+      r = sp > K ? sp - K : 0.0f;
+      break;
+    case SDEMC_PAYOFF_HESTON_RAINBOW:
+      sp = x[0];
+#pragma unroll
+      for (int i = 2; i < DIM; i += 2) sp = fmaxf(sp, x[i]);
+      r = sp > K ? sp - K : 0.0f;
+      break;
+    case SDEMC_PAYOFF_BEST_OF:
+      sp = x[0];
+#pragma unroll
+      for (int i = 1; i < DIM; ++i) sp = fmaxf(sp, x[i]);
+      r = fmaxf(sp, K);
+      break;
+    default: r = 0.0f;
+  }
+  return r * po.df;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// moment accumulation: per-thread fp64 -> warp shuffle -> shared -> per-CTA partial in the workspace ->
+// the last CTA to finish folds all partials (fixed order: deterministic) into the caller's sdemc_moments.
+// Replaces the fp32 tensor accumulators of mc.py:116-120 / mlmc.py:49-53.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kNumMoments = 8;
+
+struct Accum {
+  double v[kNumMoments];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < kNumMoments; ++i) v[i] = 0.0;
+  }
+  // p: discounted payoff (or correction), c: control value, iters: executed iterations
+  __device__ __forceinline__ void add(float p, float c, int iters) {
+    const double dp = (double)p, dc = (double)c;
+    v[0] += dp;
+    v[1] = fma(dp, dp, v[1]);
+    v[2] += dc;
+    v[3] = fma(dc, dc, v[3]);
+    v[4] = fma(dp, dc, v[4]);
+    v[5] += 1.0;
+    v[6] += (double)iters;
+  }
+};
+
+// workspace layout: [0, 64) bytes: uint32 ticket ; then gridDim.x * kNumMoments doubles
+__device__ __forceinline__ void block_reduce_and_publish(const Accum& acc, double* d_moments, void* d_ws) {
+  __shared__ double sh[32][kNumMoments];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  double v[kNumMoments];
+#pragma unroll
+  for (int i = 0; i < kNumMoments; ++i) {
+    v[i] = acc.v[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kNumMoments; ++i) sh[warp][i] = v[i];
+  }
+  __syncthreads();
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(d_ws);
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_ws) + 64);
+  if (threadIdx.x < kNumMoments) {
+    double t = 0.0;
+    for (int w = 0; w < nwarps; ++w) t += sh[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * kNumMoments + threadIdx.x] = t;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(ticket, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < kNumMoments) {
+      double t = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(&partials[(size_t)b * kNumMoments + threadIdx.x]);
+      d_moments[threadIdx.x] += t;  // accumulate across launches of one estimator (same stream => ordered)
+    }
+    if (threadIdx.x == 0) *ticket = 0u;  // re-arm for the next launch
+  }
+}
+
+}  // namespace sdemc

@@ -1,0 +1,368 @@
+// jump.cuh -- fused jump-adapted Euler kernels: JumpDiffusionSolver.solve (solvers.py:164-226) + payoff + moments.
+//
+// Semantics kept from the reference loop:
+//   h  = min(h, max(T - t, 0))            the mesh only shrinks, the grid restarts at every jump   :190
+//   dt = min(h, tau - t)                                                                       :191
+//   hit <=> |tau - t| <= 1e-12 + 1e-5 |t|   (torch.isclose with its default rtol)                :212,225
+//   the jump acts on the pre-step state unless exact_jumps                                       :214-217
+//   second Brownian driver of 'indep' models = ONE scalar normal shared by all components        :198-201
+//   payoff at array index num_steps ('terminal') or at the last state ('adapted')                mc.py:84-91
+// Deviation: dt is clamped at 0 where the reference would trip `assert next_jump_time >= t` (:193).
+#pragma once
+#include "engine.cuh"
+
+namespace sdemc {
+
+enum { JSRC_INJECT = 0, JSRC_QUEUE = 1, JSRC_INLINE = 2 };
+
+// ------------------------------------------------------------------------------------------------------------
+// Jump sources: where (tau, J) of the next jump comes from.
+//   begin_iter(k) : called at the top of loop iteration k
+//   advance()     : move to the following jump (called once before the first iteration and after every hit)
+//   mark(k)       : jump mark to apply on a hit in iteration k
+// ------------------------------------------------------------------------------------------------------------
+
+// Deterministic parity mode: sample_jump_times / sample_one_jump replaced by arrays (solvers.py:143-148).
+template <int MARKS>
+struct InjectJumps {
+  const float* jt;
+  const float* mk;
+  int jidx, max_jumps;
+  float tau;
+  __device__ __forceinline__ void init(const DevSde& s, const DevInject& inj, uint64_t i) {
+    jt = inj.jump_times + i * (uint64_t)s.max_jumps;
+    mk = inj.marks + i * (uint64_t)inj.K;
+    jidx = -1;
+    max_jumps = s.max_jumps;
+    tau = 0.0f;
+  }
+  __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys&, int) {}
+  __device__ __forceinline__ void advance(const DevSde&, const PhiloxKeys&) {
+    ++jidx;
+    tau = jidx < max_jumps ? jt[jidx] : __int_as_float(0x7f800000);
+  }
+  __device__ __forceinline__ float mark(const DevSde& s, int k) const { return mark_from_raw<MARKS>(s, mk[k]); }
+};
+
+// Sparse jumps (rate * h << 1, e.g. Merton): a per-thread queue of QD pre-drawn (tau, J) pairs in shared
+// memory, filled with full lane utilisation; the hot loop only pops.  Refill (rare) happens in place.
+template <int MARKS>
+struct QueueJumps {
+  float2* q;  // this thread's column: slot j lives at q[j * blockDim.x]
+  int qi, qd;
+  uint32_t chunk, plo, phi;
+  float tau_acc, tau, J;
+  __device__ __forceinline__ void init(float2* smem, int qdepth, uint32_t plo_, uint32_t phi_) {
+    q = smem + threadIdx.x;
+    qd = qdepth;
+    qi = qdepth - 1;  // first advance() triggers the initial fill
+    chunk = 0;
+    plo = plo_;
+    phi = phi_;
+    tau_acc = 0.0f;
+    tau = 0.0f;
+    J = 0.0f;
+  }
+  __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys&, int) {}
+  __device__ __forceinline__ void fill(const DevSde& s, const PhiloxKeys& keys) {
+    const int groups = qd >> 2;
+    for (int r = 0; r < groups; ++r) {
+      uint32_t g[4], m[4];
+      const uint32_t blk = (chunk * (uint32_t)groups + (uint32_t)r) * 2u;
+      philox4x32_10(blk, STREAM_JUMP_QUEUE, plo, phi, keys, g);
+      philox4x32_10(blk + 1u, STREAM_JUMP_QUEUE, plo, phi, keys, m);
+      float raw[4];
+      if (MARKS == SDEMC_MARKS_LOGNORMAL) {
+        box_muller(m[0], m[1], raw[0], raw[1]);
+        box_muller(m[2], m[3], raw[2], raw[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) raw[j] = bits_to_u01(m[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        tau_acc = fmaf(exp1_from_bits(g[j]), s.inv_rate, tau_acc);
+        q[(r * 4 + j) * blockDim.x] = make_float2(tau_acc, mark_from_raw<MARKS>(s, raw[j]));
+      }
+    }
+    ++chunk;
+  }
+  __device__ __forceinline__ void advance(const DevSde& s, const PhiloxKeys& keys) {
+    ++qi;
+    if (qi == qd) {
+      fill(s, keys);
+      qi = 0;
+    }
+    const float2 e = q[qi * blockDim.x];
+    tau = e.x;
+    J = e.y;
+  }
+  __device__ __forceinline__ float mark(const DevSde&, int) const { return J; }
+};
+
+// Dense jumps (rate * h ~ 1, e.g. the Levy models): every iteration draws a fresh (gap, mark) candidate in
+// registers and a hit consumes it -- branch-free, no divergence, no queue.
+template <int MARKS>
+struct InlineJumps {
+  uint32_t plo, phi;
+  float tau, J, cand_gap, cand_raw;
+  __device__ __forceinline__ void init(uint32_t plo_, uint32_t phi_) {
+    plo = plo_;
+    phi = phi_;
+    tau = 0.0f;
+    J = 0.0f;
+  }
+  __device__ __forceinline__ void draw(const PhiloxKeys& keys, uint32_t blk) {
+    uint32_t o[4];
+    philox4x32_10(blk, STREAM_JUMP_INLINE, plo, phi, keys, o);
+    cand_gap = exp1_from_bits(o[0]);
+    if (MARKS == SDEMC_MARKS_LOGNORMAL) {
+      float unused;
+      box_muller(o[1], o[2], cand_raw, unused);
+    } else {
+      cand_raw = bits_to_u01(o[1]);
+    }
+  }
+  __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys& keys, int k) { draw(keys, (uint32_t)k); }
+  __device__ __forceinline__ void advance(const DevSde& s, const PhiloxKeys&) {
+    tau = fmaf(cand_gap, s.inv_rate, tau);
+    J = mark_from_raw<MARKS>(s, cand_raw);
+  }
+  __device__ __forceinline__ float mark(const DevSde&, int) const { return J; }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// per-path state and one loop iteration
+// ------------------------------------------------------------------------------------------------------------
+struct JumpState {
+  float x[kMaxDim];
+  float t, h;
+  int k;
+  bool need_pop;
+};
+
+// one iteration of the while-loop solvers.py:182-225.  zn: this iteration's unit normals
+// (BASE correlated-driver normals, then the common second-driver normal if M == 2).
+template <class C, class Src, bool STORE>
+__device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys& keys, JumpState& st, Src& src,
+                                               const float* zn, const DevOut& out, uint64_t row, float extra_z) {
+  constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M;
+  src.begin_iter(s, keys, st.k);
+  if (st.need_pop) src.advance(s, keys);
+  const float tau = src.tau;
+  st.h = fminf(st.h, fmaxf(s.T - st.t, 0.0f));
+  const float dt = fmaxf(fminf(st.h, tau - st.t), 0.0f);
+  const float sq = fast_sqrt(dt);
+  float z1[kMaxDim], w1[kMaxDim], w2[kMaxDim], xo[kMaxDim];
+#pragma unroll
+  for (int i = 0; i < BASE; ++i) z1[i] = zn[i];
+  correlate<C>(s, z1, w1);
+#pragma unroll
+  for (int i = 0; i < BASE; ++i) w2[i] = M == 2 ? zn[BASE] : 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxDim; ++i) xo[i] = st.x[i];
+  euler_step<C>(s, st.x, dt, sq, w1, w2);
+  st.t += dt;
+  const bool hit = fabsf(tau - st.t) <= fmaf(fabsf(st.t), 1e-5f, 1e-12f);
+  float Jc = 0.0f;
+  if (STORE && out.left) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) out.left[(row * (uint64_t)(out.S + 1) + st.k + 1) * DIM + d] = st.x[d];
+  }
+  if (hit) {
+    Jc = src.mark(s, st.k);
+    if (s.exact_jumps) add_jump<C>(s, st.x, st.x, Jc);
+    else add_jump<C>(s, st.x, xo, Jc);
+  }
+  st.need_pop = hit;
+  if (STORE) {
+    const uint64_t o1 = row * (uint64_t)(out.S + 1) + st.k + 1;
+    if (out.paths) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) out.paths[o1 * DIM + d] = st.x[d];
+    }
+    if (out.jumps) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) out.jumps[o1 * DIM + d] = Jc;
+    }
+    if (out.times) out.times[o1] = st.t;
+    if (out.normals) {
+      float* np = out.normals + (row * (uint64_t)out.S + st.k) * (DIM * M);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const float wd = d < BASE ? w1[d] * sq : extra_z * sq;
+        np[d * M] = wd;
+        if (M == 2) np[d * M + 1] = w2[d < BASE ? d : 0] * sq;
+      }
+    }
+  }
+  ++st.k;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------------------
+template <class C, int JSRC, bool STORE>
+__global__ void __launch_bounds__(256) jump_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+                                                   const PhiloxKeys keys, const DevInject inj, const DevOut out,
+                                                   const int qdepth, double* __restrict__ d_moments,
+                                                   void* __restrict__ d_ws) {
+  constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M, MARKS = C::MARKS;
+  constexpr int NZ = BASE + (M == 2 ? 1 : 0);  // normals per iteration
+  constexpr int NZP = pad_pow2(NZ);
+  constexpr int SPB = NZP <= 4 ? 4 / NZP : 1;
+  constexpr int BPS = NZP <= 4 ? 1 : NZP / 4;
+  constexpr bool INJECT = JSRC == JSRC_INJECT;
+  using Src = typename std::conditional<JSRC == JSRC_INJECT, InjectJumps<MARKS>,
+                                        typename std::conditional<JSRC == JSRC_QUEUE, QueueJumps<MARKS>,
+                                                                  InlineJumps<MARKS>>::type>::type;
+  extern __shared__ float2 jump_queue_smem[];
+
+  Accum acc;
+  acc.zero();
+  int local_max_iters = 0;
+  const int n = s.num_steps;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
+    const uint64_t gp = rg.path_lo + i;
+    const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
+    JumpState st;
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) st.x[d] = d < DIM ? s.x0[d] : 0.0f;
+    st.t = 0.0f;
+    st.h = s.h0;
+    st.k = 0;
+    st.need_pop = true;
+    Src src;
+    if constexpr (JSRC == JSRC_INJECT) src.init(s, inj, i);
+    else if constexpr (JSRC == JSRC_QUEUE) src.init(jump_queue_smem, qdepth, plo, phi);
+    else src.init(plo, phi);
+
+    // fetch the unit normals of SPB consecutive iterations starting at iteration b * SPB
+    auto load_normals = [&](int b, float(&nrm)[SPB * NZP], float(&extra)[SPB]) {
+      if (!INJECT) {
+#pragma unroll
+        for (int r = 0; r < BPS; ++r) {
+          uint32_t o[4];
+          philox4x32_10((uint32_t)(b * BPS + r), STREAM_DIFFUSION, plo, phi, keys, o);
+          box_muller(o[0], o[1], nrm[4 * r + 0], nrm[4 * r + 1]);
+          box_muller(o[2], o[3], nrm[4 * r + 2], nrm[4 * r + 3]);
+        }
+#pragma unroll
+        for (int sp = 0; sp < SPB; ++sp) extra[sp] = 0.0f;
+      } else {
+#pragma unroll
+        for (int sp = 0; sp < SPB; ++sp) {
+          const int k = b * SPB + sp;
+          extra[sp] = 0.0f;
+#pragma unroll
+          for (int q = 0; q < NZP; ++q) nrm[sp * NZP + q] = 0.0f;
+          if (k < inj.K) {
+            const float* zp = inj.z + (i * (uint64_t)inj.K + k) * DIM;
+#pragma unroll
+            for (int q = 0; q < BASE; ++q) nrm[sp * NZP + q] = zp[q];
+            if (C::ASIAN) extra[sp] = zp[BASE];
+            if (M == 2) nrm[sp * NZP + BASE] = inj.zc[i * (uint64_t)inj.K + k];
+          }
+        }
+      }
+    };
+
+    float xs[kMaxDim];  // state at array index num_steps ('terminal' payoff index)
+    int own_iters = 0;
+    if (STORE) {
+      // lock-step over the whole allocation: finished paths idle with dt = 0 exactly as in the reference,
+      // where the loop runs until the slowest path of the batch is done (:182).
+      if (out.paths) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) out.paths[(i * (uint64_t)(out.S + 1)) * DIM + d] = st.x[d];
+      }
+      if (out.left) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) out.left[(i * (uint64_t)(out.S + 1)) * DIM + d] = st.x[d];
+      }
+      if (out.jumps) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) out.jumps[(i * (uint64_t)(out.S + 1)) * DIM + d] = 0.0f;
+      }
+      if (out.times) out.times[i * (uint64_t)(out.S + 1)] = 0.0f;
+#pragma unroll
+      for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
+      for (int b = 0; b * SPB < out.S; ++b) {
+        float nrm[SPB * NZP], extra[SPB];
+        load_normals(b, nrm, extra);
+#pragma unroll
+        for (int sp = 0; sp < SPB; ++sp) {
+          if (st.k < out.S) {
+            if (st.t < s.T) own_iters = st.k + 1;
+            jump_iteration<C, Src, true>(s, keys, st, src, nrm + sp * NZP, out, i, extra[sp]);
+            if (st.k == n) {
+#pragma unroll
+              for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
+            }
+          }
+        }
+      }
+    } else {
+      // phase 1: the first num_steps iterations can never reach T (each advances by at most T/num_steps),
+      // so full Philox blocks run without the loop-exit test.
+      const int nb_full = n / SPB;
+      for (int b = 0; b < nb_full; ++b) {
+        float nrm[SPB * NZP], extra[SPB];
+        load_normals(b, nrm, extra);
+#pragma unroll
+        for (int sp = 0; sp < SPB; ++sp) jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZP, out, i, 0.0f);
+      }
+      if (st.k == n) {
+#pragma unroll
+        for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
+      }
+      // phase 2: remaining iterations (the extra ones forced by jumps) with the exit test
+      const int kcap = INJECT ? inj.K : 4 * (n + s.max_jumps) + 64;
+      bool done = false;
+      for (int b = nb_full; !done; ++b) {
+        float nrm[SPB * NZP], extra[SPB];
+        load_normals(b, nrm, extra);
+#pragma unroll
+        for (int sp = 0; sp < SPB; ++sp) {
+          if (!done) {
+            if (!(st.t < s.T) || st.k >= kcap) {
+              done = true;
+            } else {
+              jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZP, out, i, 0.0f);
+              if (st.k == n) {
+#pragma unroll
+                for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
+              }
+            }
+          }
+        }
+      }
+      own_iters = st.k;
+    }
+
+    float xp[kMaxDim];
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) xp[d] = po.index_mode == SDEMC_INDEX_TERMINAL ? xs[d] : st.x[d];
+    const float pay = eval_payoff<DIM>(po, xp);
+    if (STORE) {
+      if (out.payoffs) out.payoffs[i] = pay;
+      if (out.iters) out.iters[i] = own_iters;
+      local_max_iters = max(local_max_iters, own_iters);
+    } else {
+      acc.add(pay, po.df * st.x[0] - s.x0[0], own_iters);
+    }
+  }
+  if (STORE) {
+    if (out.total_steps) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+        local_max_iters = max(local_max_iters, __shfl_xor_sync(0xffffffffu, local_max_iters, off));
+      if ((threadIdx.x & 31) == 0 && local_max_iters > 0) atomicMax(out.total_steps, local_max_iters);
+    }
+  } else {
+    block_reduce_and_publish(acc, d_moments, d_ws);
+  }
+}
+
+}  // namespace sdemc

@@ -1,0 +1,25 @@
+// launch.cuh -- entry points of the per-solver translation units (internal, C++)
+#pragma once
+#include "host_common.cuh"
+
+namespace sdemc {
+
+struct LaunchArgs {
+  DevSde sde;
+  DevPayoff payoff;
+  DevRange range;
+  PhiloxKeys keys;
+  DevInject inject;
+  DevOut out;
+  bool use_inject;
+  bool store;
+  int qdepth;          // jump queue depth (multiple of 4), 0 => inline jump strategy
+  double* d_moments;
+  void* d_ws;
+  cudaStream_t stream;
+};
+
+int launch_diffusion(const sdemc_sde& s, const LaunchArgs& a);
+int launch_jump(const sdemc_sde& s, const LaunchArgs& a);
+
+}  // namespace sdemc

@@ -1,0 +1,60 @@
+// launch_jump.cu -- instantiation + dispatch of the jump-adapted kernels (jump.cuh)
+#include <type_traits>
+
+#include "jump.cuh"
+#include "launch.cuh"
+
+namespace sdemc {
+namespace {
+
+template <class C, int JSRC, bool STORE>
+int run(const LaunchArgs& a) {
+  auto kernel = jump_kernel<C, JSRC, STORE>;
+  const size_t smem = JSRC == JSRC_QUEUE ? (size_t)a.qdepth * kBlock * sizeof(float2) : 0;
+  if (smem > 48 * 1024) SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = 0;
+  int rc = pick_grid(kernel, smem, a.range.n_paths, &grid);
+  if (rc != SDEMC_OK) return rc;
+  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, a.qdepth, a.d_moments,
+                                           a.d_ws);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+
+template <class C>
+int by_mode(const LaunchArgs& a) {
+  if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;
+  if (a.qdepth > 0) return a.store ? run<C, JSRC_QUEUE, true>(a) : run<C, JSRC_QUEUE, false>(a);
+  return a.store ? run<C, JSRC_INLINE, true>(a) : run<C, JSRC_INLINE, false>(a);
+}
+
+template <int FAMILY, int M, int MARKS>
+int by_dim(const sdemc_sde& s, const LaunchArgs& a) {
+  switch (s.dim) {
+    case 1: return by_mode<Cfg<FAMILY, 1, M, MARKS, false>>(a);
+    case 2: return by_mode<Cfg<FAMILY, 2, M, MARKS, false>>(a);
+    case 3: return by_mode<Cfg<FAMILY, 3, M, MARKS, false>>(a);
+    case 4: return by_mode<Cfg<FAMILY, 4, M, MARKS, false>>(a);
+  }
+  return SDEMC_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int launch_jump(const sdemc_sde& s, const LaunchArgs& a) {
+  if (a.qdepth < 0 || (a.qdepth & 3) || a.qdepth > 64) return SDEMC_ERR_BAD_ARG;
+  if (s.asian) {
+    if (s.dim == 2 && s.m == 1 && s.family == SDEMC_FAMILY_GEOMETRIC && s.marks == SDEMC_MARKS_LOGNORMAL)
+      return by_mode<Cfg<SDEMC_FAMILY_GEOMETRIC, 2, 1, SDEMC_MARKS_LOGNORMAL, true>>(a);
+    return SDEMC_ERR_UNSUPPORTED;
+  }
+  if (s.family == SDEMC_FAMILY_GEOMETRIC && s.m == 1 && s.marks == SDEMC_MARKS_LOGNORMAL)
+    return by_dim<SDEMC_FAMILY_GEOMETRIC, 1, SDEMC_MARKS_LOGNORMAL>(s, a);
+  if (s.family == SDEMC_FAMILY_GEOMETRIC && s.m == 2 && s.marks == SDEMC_MARKS_ICDF)
+    return by_dim<SDEMC_FAMILY_GEOMETRIC, 2, SDEMC_MARKS_ICDF>(s, a);
+  if (s.family == SDEMC_FAMILY_ARITHMETIC && s.m == 2 && s.marks == SDEMC_MARKS_ICDF)
+    return by_dim<SDEMC_FAMILY_ARITHMETIC, 2, SDEMC_MARKS_ICDF>(s, a);
+  return SDEMC_ERR_UNSUPPORTED;
+}
+
+}  // namespace sdemc
