@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) diffusion_kernel(const DevSde s, const De
   constexpr int NZP = pad_pow2(NZ);       // padded to a divisor / multiple of the 4-word Philox block
   constexpr int SPB = NZP <= 4 ? 4 / NZP : 1;  // steps served by one group of blocks
   constexpr int BPS = NZP <= 4 ? 1 : NZP / 4;  // Philox blocks per group
+  constexpr bool FAST1D = DIM == 1 && M == 1 && !HESTON && !INJECT && !STORE;
   const int S = s.num_steps;
 
   Accum acc;
@@ -32,7 +33,32 @@ __global__ void __launch_bounds__(256) diffusion_kernel(const DevSde s, const De
       for (int d = 0; d < DIM; ++d) out.paths[(i * (uint64_t)(S + 1)) * DIM + d] = x[d];
     }
 
-    for (int b = 0; b * SPB < S; ++b) {
+    int b_first = 0;
+    if constexpr (FAST1D) {
+      // 1-D single-driver moments path (GBM / log-GBM): sigma sqrt(h) is folded into the Box-Muller radius and
+      // full Philox blocks (4 steps) run without per-step predicates: 2 FFMA per step on top of the normal.
+      const int nb_full = S >> 2;
+      for (int b = 0; b < nb_full; ++b) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)b, STREAM_DIFFUSION, plo, phi, keys, o);
+        float r0, c0, s0, r1, c1, s1;
+        box_muller_polar(o[0], o[1], s.neg2ln2_b1s2, r0, c0, s0);
+        box_muller_polar(o[2], o[3], s.neg2ln2_b1s2, r1, c1, s1);
+        const float g0 = fmaf(r0, c0, s.ah[0]), g1 = fmaf(r0, s0, s.ah[0]);
+        const float g2 = fmaf(r1, c1, s.ah[0]), g3 = fmaf(r1, s1, s.ah[0]);
+        if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
+          x[0] = fmaf(x[0], g0, x[0]);
+          x[0] = fmaf(x[0], g1, x[0]);
+          x[0] = fmaf(x[0], g2, x[0]);
+          x[0] = fmaf(x[0], g3, x[0]);
+        } else {
+          x[0] += (g0 + g1) + (g2 + g3);
+        }
+      }
+      b_first = nb_full;  // the generic loop below finishes the S % 4 remaining steps
+    }
+
+    for (int b = b_first; b * SPB < S; ++b) {
       float nrm[SPB * NZP];
       float extra[SPB];  // injected normal of the asian integral component (recorded, never used)
       if (!INJECT) {

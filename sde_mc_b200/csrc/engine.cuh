@@ -23,8 +23,9 @@ struct DevSde {
   float x0[kMaxDim];
   float chol[kMaxDim * kMaxDim];
   float a[kMaxDim], b1[kMaxDim], b2[kMaxDim], c[kMaxDim];
-  // uniform-grid constants: geometric 1 + a h, arithmetic a h ; b * sqrt(h)
+  // uniform-grid constants: a h ; b * sqrt(h)
   float ah[kMaxDim], b1s[kMaxDim], b2s[kMaxDim];
+  float neg2ln2_b1s2;  // -2 ln2 (b1 sqrt h)^2 for the 1-D path that folds the volatility into the Box-Muller radius
   float rate, inv_rate;
   // lognormal marks  J = 2^(z * g2 + a2) - 1
   float ln_a2, ln_g2;
@@ -107,6 +108,10 @@ __device__ __forceinline__ float mark_from_raw(const DevSde& s, float raw) {
 // w[j][i] = sum_k L[i][k] z[k][j]   (torch.matmul(lower_cholesky, normals) solvers.py:54), unit variance
 template <class C>
 __device__ __forceinline__ void correlate(const DevSde& s, const float (&z)[kMaxDim], float (&w)[kMaxDim]) {
+  if (C::BASE == 1) {  // lower_cholesky is [[1.]] for a single driven component (solvers.py:33-36)
+    w[0] = z[0];
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < C::BASE; ++i) {
     float acc = s.chol[i * kMaxDim] * z[0];
@@ -125,37 +130,28 @@ __device__ __forceinline__ void euler_step(const DevSde& s, float (&x)[kMaxDim],
   const float x_first = x[0];
 #pragma unroll
   for (int i = 0; i < C::BASE; ++i) {
-    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
-      float g = fmaf(s.a[i], dt, 1.0f);
-      g = fmaf(s.b1[i] * sq, w1[i], g);
-      if (C::M == 2) g = fmaf(s.b2[i] * sq, w2[i], g);
-      x[i] *= g;
-    } else {
-      float v = fmaf(s.a[i], dt, x[i]);
-      v = fmaf(s.b1[i] * sq, w1[i], v);
-      if (C::M == 2) v = fmaf(s.b2[i] * sq, w2[i], v);
-      x[i] = v;
-    }
+    // relative increment g = a dt + b1 sq w1 (+ b2 sq w2).  Keeping g small and adding it with one FMA
+    // (x + x g) avoids the systematic rounding of a pre-added (1 + a dt) constant over hundreds of steps.
+    float g = s.a[i] * dt;
+    g = fmaf(s.b1[i] * sq, w1[i], g);
+    if (C::M == 2) g = fmaf(s.b2[i] * sq, w2[i], g);
+    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) x[i] = fmaf(x[i], g, x[i]);
+    else x[i] += g;
   }
   if (C::ASIAN) x[C::DIM - 1] = fmaf(x_first, dt, x[C::DIM - 1]);  // AsianWrapper.drift sde.py:396-397
 }
 
-// same, on the uniform grid of DiffusionSolver (h, sqrt(h) folded into per-launch constants)
+// same, on the uniform grid of DiffusionSolver (h, sqrt(h) folded into per-launch constants ah = a h, b*s = b sqrt(h))
 template <class C>
 __device__ __forceinline__ void euler_step_uniform(const DevSde& s, float (&x)[kMaxDim], const float (&w1)[kMaxDim],
                                                    const float (&w2)[kMaxDim]) {
   const float x_first = x[0];
 #pragma unroll
   for (int i = 0; i < C::BASE; ++i) {
-    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
-      float g = fmaf(s.b1s[i], w1[i], s.ah[i]);
-      if (C::M == 2) g = fmaf(s.b2s[i], w2[i], g);
-      x[i] *= g;
-    } else {
-      float v = fmaf(s.b1s[i], w1[i], x[i] + s.ah[i]);
-      if (C::M == 2) v = fmaf(s.b2s[i], w2[i], v);
-      x[i] = v;
-    }
+    float g = fmaf(s.b1s[i], w1[i], s.ah[i]);
+    if (C::M == 2) g = fmaf(s.b2s[i], w2[i], g);
+    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) x[i] = fmaf(x[i], g, x[i]);
+    else x[i] += g;
   }
   if (C::ASIAN) x[C::DIM - 1] = fmaf(x_first, s.h0, x[C::DIM - 1]);
 }

@@ -51,10 +51,11 @@ inline DevSde to_dev(const sdemc_sde& s, int num_steps) {
     d.b1[i] = s.b1[i];
     d.b2[i] = s.b2[i];
     d.c[i] = s.c[i];
-    d.ah[i] = s.family == SDEMC_FAMILY_GEOMETRIC ? 1.0f + s.a[i] * d.h0 : s.a[i] * d.h0;
+    d.ah[i] = s.a[i] * d.h0;
     d.b1s[i] = s.b1[i] * d.sqrt_h0;
     d.b2s[i] = s.b2[i] * d.sqrt_h0;
   }
+  d.neg2ln2_b1s2 = -1.3862943611198906f * d.b1s[0] * d.b1s[0];
   for (int i = 0; i < kMaxDim * kMaxDim; ++i) d.chol[i] = s.chol[i];
   d.rate = s.rate;
   d.inv_rate = s.rate > 0.0f ? 1.0f / s.rate : 0.0f;

@@ -15,6 +15,19 @@ namespace sdemc {
 
 enum { JSRC_INJECT = 0, JSRC_QUEUE = 1, JSRC_INLINE = 2 };
 
+// Shared memory of the sparse-jump queue.  Always addressed as an offset from the symbol (plain LDS/STS with a
+// register index); holding a generic pointer to it would make ptxas rebuild the shared-window address
+// (S2R SR_CgaCtaId + LEA) on every loop iteration.
+extern __shared__ float2 jump_queue_smem[];
+__device__ __forceinline__ float2 lds_float2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+// Block-shared copies of the problem for the out-of-line refill (a __noinline__ function cannot see kernel params).
+__shared__ DevSde g_sh_sde;
+__shared__ PhiloxKeys g_sh_keys;
+
 // ------------------------------------------------------------------------------------------------------------
 // Jump sources: where (tau, J) of the next jump comes from.
 //   begin_iter(k) : called at the top of loop iteration k
@@ -27,35 +40,72 @@ template <int MARKS>
 struct InjectJumps {
   const float* jt;
   const float* mk;
-  int jidx, max_jumps;
+  int jidx, max_jumps, K;
   float tau;
   __device__ __forceinline__ void init(const DevSde& s, const DevInject& inj, uint64_t i) {
     jt = inj.jump_times + i * (uint64_t)s.max_jumps;
     mk = inj.marks + i * (uint64_t)inj.K;
     jidx = -1;
     max_jumps = s.max_jumps;
+    K = inj.K;
     tau = 0.0f;
   }
   __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys&, int) {}
-  __device__ __forceinline__ void advance(const DevSde&, const PhiloxKeys&) {
-    ++jidx;
-    tau = jidx < max_jumps ? jt[jidx] : __int_as_float(0x7f800000);
+  __device__ __forceinline__ void advance(const DevSde&, const PhiloxKeys&, bool pop) {
+    if (pop) {
+      ++jidx;
+      tau = jidx < max_jumps ? jt[jidx] : __int_as_float(0x7f800000);
+    }
   }
-  __device__ __forceinline__ float mark(const DevSde& s, int k) const { return mark_from_raw<MARKS>(s, mk[k]); }
+  __device__ __forceinline__ float mark(const DevSde& s, int k) const {
+    return mark_from_raw<MARKS>(s, k < K ? mk[k] : 0.0f);
+  }
 };
 
+// Cold path of the sparse-jump queue, deliberately out of line (one copy per kernel instead of one per unrolled
+// iteration): draws `qd` more (tau, J) pairs into this thread's queue column and returns the new running jump time.
+// Two Philox blocks give 4 jumps: 4 gap uniforms + 4 mark draws (2 Box-Muller pairs or 4 uniforms).
+template <int MARKS>
+__device__ __noinline__ float queue_refill(int qd, uint32_t chunk, uint32_t plo, uint32_t phi, float tau_acc) {
+  const DevSde& s = g_sh_sde;
+  const PhiloxKeys& keys = g_sh_keys;
+  const int groups = qd >> 2;
+  for (int r = 0; r < groups; ++r) {
+    uint32_t g[4], m[4];
+    const uint32_t blk = (chunk * (uint32_t)groups + (uint32_t)r) * 2u;
+    philox4x32_10(blk, STREAM_JUMP_QUEUE, plo, phi, keys, g);
+    philox4x32_10(blk + 1u, STREAM_JUMP_QUEUE, plo, phi, keys, m);
+    float raw[4];
+    if (MARKS == SDEMC_MARKS_LOGNORMAL) {
+      box_muller(m[0], m[1], raw[0], raw[1]);
+      box_muller(m[2], m[3], raw[2], raw[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) raw[j] = bits_to_u01(m[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tau_acc = fmaf(exp1_from_bits(g[j]), s.inv_rate, tau_acc);
+      jump_queue_smem[(r * 4 + j) * blockDim.x + threadIdx.x] = make_float2(tau_acc, mark_from_raw<MARKS>(s, raw[j]));
+    }
+  }
+  return tau_acc;
+}
+
 // Sparse jumps (rate * h << 1, e.g. Merton): a per-thread queue of QD pre-drawn (tau, J) pairs in shared
-// memory, filled with full lane utilisation; the hot loop only pops.  Refill (rare) happens in place.
+// memory, filled with full lane utilisation.  The hot loop is branch-free: qi += hit, one LDS.64 per iteration.
 template <int MARKS>
 struct QueueJumps {
-  float2* q;  // this thread's column: slot j lives at q[j * blockDim.x]
+  // this thread's column: slot j lives at jump_queue_smem[j * blockDim.x + threadIdx.x]; the hot loop reads it
+  // through a 32-bit shared-window address kept in a register (base + qi * stride, one IMAD + one LDS.64)
   int qi, qd;
-  uint32_t chunk, plo, phi;
+  uint32_t chunk, plo, phi, q_base, q_stride;
   float tau_acc, tau, J;
-  __device__ __forceinline__ void init(float2* smem, int qdepth, uint32_t plo_, uint32_t phi_) {
-    q = smem + threadIdx.x;
+  __device__ __forceinline__ void init(int qdepth, uint32_t plo_, uint32_t phi_) {
+    q_base = (uint32_t)__cvta_generic_to_shared(&jump_queue_smem[threadIdx.x]);
+    q_stride = blockDim.x * (uint32_t)sizeof(float2);
     qd = qdepth;
-    qi = qdepth - 1;  // first advance() triggers the initial fill
+    qi = qdepth - 1;  // the first advance(pop = true) triggers the initial fill
     chunk = 0;
     plo = plo_;
     phi = phi_;
@@ -64,36 +114,14 @@ struct QueueJumps {
     J = 0.0f;
   }
   __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys&, int) {}
-  __device__ __forceinline__ void fill(const DevSde& s, const PhiloxKeys& keys) {
-    const int groups = qd >> 2;
-    for (int r = 0; r < groups; ++r) {
-      uint32_t g[4], m[4];
-      const uint32_t blk = (chunk * (uint32_t)groups + (uint32_t)r) * 2u;
-      philox4x32_10(blk, STREAM_JUMP_QUEUE, plo, phi, keys, g);
-      philox4x32_10(blk + 1u, STREAM_JUMP_QUEUE, plo, phi, keys, m);
-      float raw[4];
-      if (MARKS == SDEMC_MARKS_LOGNORMAL) {
-        box_muller(m[0], m[1], raw[0], raw[1]);
-        box_muller(m[2], m[3], raw[2], raw[3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) raw[j] = bits_to_u01(m[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        tau_acc = fmaf(exp1_from_bits(g[j]), s.inv_rate, tau_acc);
-        q[(r * 4 + j) * blockDim.x] = make_float2(tau_acc, mark_from_raw<MARKS>(s, raw[j]));
-      }
-    }
-    ++chunk;
-  }
-  __device__ __forceinline__ void advance(const DevSde& s, const PhiloxKeys& keys) {
-    ++qi;
+  __device__ __forceinline__ void advance(const DevSde&, const PhiloxKeys&, bool pop) {
+    qi += pop ? 1 : 0;
     if (qi == qd) {
-      fill(s, keys);
+      tau_acc = queue_refill<MARKS>(qd, chunk, plo, phi, tau_acc);
+      ++chunk;
       qi = 0;
     }
-    const float2 e = q[qi * blockDim.x];
+    const float2 e = lds_float2(q_base + (uint32_t)qi * q_stride);
     tau = e.x;
     J = e.y;
   }
@@ -112,9 +140,9 @@ struct InlineJumps {
     tau = 0.0f;
     J = 0.0f;
   }
-  __device__ __forceinline__ void draw(const PhiloxKeys& keys, uint32_t blk) {
+  __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys& keys, int k) {
     uint32_t o[4];
-    philox4x32_10(blk, STREAM_JUMP_INLINE, plo, phi, keys, o);
+    philox4x32_10((uint32_t)k, STREAM_JUMP_INLINE, plo, phi, keys, o);
     cand_gap = exp1_from_bits(o[0]);
     if (MARKS == SDEMC_MARKS_LOGNORMAL) {
       float unused;
@@ -123,10 +151,11 @@ struct InlineJumps {
       cand_raw = bits_to_u01(o[1]);
     }
   }
-  __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys& keys, int k) { draw(keys, (uint32_t)k); }
-  __device__ __forceinline__ void advance(const DevSde& s, const PhiloxKeys&) {
-    tau = fmaf(cand_gap, s.inv_rate, tau);
-    J = mark_from_raw<MARKS>(s, cand_raw);
+  __device__ __forceinline__ void advance(const DevSde& s, const PhiloxKeys&, bool pop) {
+    const float t2 = fmaf(cand_gap, s.inv_rate, tau);
+    const float j2 = mark_from_raw<MARKS>(s, cand_raw);
+    tau = pop ? t2 : tau;
+    J = pop ? j2 : J;
   }
   __device__ __forceinline__ float mark(const DevSde&, int) const { return J; }
 };
@@ -148,7 +177,7 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
                                                const float* zn, const DevOut& out, uint64_t row, float extra_z) {
   constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M;
   src.begin_iter(s, keys, st.k);
-  if (st.need_pop) src.advance(s, keys);
+  src.advance(s, keys, st.need_pop);
   const float tau = src.tau;
   st.h = fminf(st.h, fmaxf(s.T - st.t, 0.0f));
   const float dt = fmaxf(fminf(st.h, tau - st.t), 0.0f);
@@ -164,16 +193,17 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
   euler_step<C>(s, st.x, dt, sq, w1, w2);
   st.t += dt;
   const bool hit = fabsf(tau - st.t) <= fmaf(fabsf(st.t), 1e-5f, 1e-12f);
-  float Jc = 0.0f;
   if (STORE && out.left) {
 #pragma unroll
     for (int d = 0; d < DIM; ++d) out.left[(row * (uint64_t)(out.S + 1) + st.k + 1) * DIM + d] = st.x[d];
   }
-  if (hit) {
-    Jc = src.mark(s, st.k);
-    if (s.exact_jumps) add_jump<C>(s, st.x, st.x, Jc);
-    else add_jump<C>(s, st.x, xo, Jc);
+  // branch-free: a zero mark leaves the state untouched (x + c x_base * 0)
+  const float Jc = hit ? src.mark(s, st.k) : 0.0f;
+  if (s.exact_jumps) {
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) xo[i] = st.x[i];
   }
+  add_jump<C>(s, st.x, xo, Jc);
   st.need_pop = hit;
   if (STORE) {
     const uint64_t o1 = row * (uint64_t)(out.S + 1) + st.k + 1;
@@ -202,8 +232,11 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
 // ------------------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------------------
+#ifndef SDEMC_JUMP_MIN_BLOCKS
+#define SDEMC_JUMP_MIN_BLOCKS 4  // <= 64 registers per thread: 32 resident warps per SM
+#endif
 template <class C, int JSRC, bool STORE>
-__global__ void __launch_bounds__(256) jump_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+__global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                    const PhiloxKeys keys, const DevInject inj, const DevOut out,
                                                    const int qdepth, double* __restrict__ d_moments,
                                                    void* __restrict__ d_ws) {
@@ -216,7 +249,13 @@ __global__ void __launch_bounds__(256) jump_kernel(const DevSde s, const DevPayo
   using Src = typename std::conditional<JSRC == JSRC_INJECT, InjectJumps<MARKS>,
                                         typename std::conditional<JSRC == JSRC_QUEUE, QueueJumps<MARKS>,
                                                                   InlineJumps<MARKS>>::type>::type;
-  extern __shared__ float2 jump_queue_smem[];
+  if (JSRC == JSRC_QUEUE) {
+    if (threadIdx.x == 0) {
+      g_sh_sde = s;
+      g_sh_keys = keys;
+    }
+    __syncthreads();
+  }
 
   Accum acc;
   acc.zero();
@@ -235,7 +274,7 @@ __global__ void __launch_bounds__(256) jump_kernel(const DevSde s, const DevPayo
     st.need_pop = true;
     Src src;
     if constexpr (JSRC == JSRC_INJECT) src.init(s, inj, i);
-    else if constexpr (JSRC == JSRC_QUEUE) src.init(jump_queue_smem, qdepth, plo, phi);
+    else if constexpr (JSRC == JSRC_QUEUE) src.init(qdepth, plo, phi);
     else src.init(plo, phi);
 
     // fetch the unit normals of SPB consecutive iterations starting at iteration b * SPB
@@ -317,25 +356,26 @@ __global__ void __launch_bounds__(256) jump_kernel(const DevSde s, const DevPayo
 #pragma unroll
         for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
       }
-      // phase 2: remaining iterations (the extra ones forced by jumps) with the exit test
+      // phase 2: the few remaining iterations (those forced by jumps), one per trip with the exit test.  The
+      // iteration's Philox block is regenerated and its lane selected, so the stream stays identical to STORE mode.
       const int kcap = INJECT ? inj.K : 4 * (n + s.max_jumps) + 64;
-      bool done = false;
-      for (int b = nb_full; !done; ++b) {
-        float nrm[SPB * NZP], extra[SPB];
-        load_normals(b, nrm, extra);
+      while (st.t < s.T && st.k < kcap) {
+        float nrm[SPB * NZP], extra[SPB], zn[NZP];
+        load_normals(st.k / SPB, nrm, extra);
+        const int sp_dyn = st.k % SPB;
 #pragma unroll
-        for (int sp = 0; sp < SPB; ++sp) {
-          if (!done) {
-            if (!(st.t < s.T) || st.k >= kcap) {
-              done = true;
-            } else {
-              jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZP, out, i, 0.0f);
-              if (st.k == n) {
+        for (int q = 0; q < NZP; ++q) zn[q] = nrm[q];
 #pragma unroll
-                for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
-              }
-            }
+        for (int sp = 1; sp < SPB; ++sp) {
+          if (sp == sp_dyn) {
+#pragma unroll
+            for (int q = 0; q < NZP; ++q) zn[q] = nrm[sp * NZP + q];
           }
+        }
+        jump_iteration<C, Src, false>(s, keys, st, src, zn, out, i, 0.0f);
+        if (st.k == n) {
+#pragma unroll
+          for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
         }
       }
       own_iters = st.k;

@@ -53,7 +53,12 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 // 23 random mantissa bits -> float in [1, 2).  No I2F (that would go to the XU pipe).
-__device__ __forceinline__ float bits_to_12(uint32_t u) { return __uint_as_float((u & 0x007fffffu) | 0x3f800000u); }
+// One LOP3 ((u & mask) | one, LUT 0xEA) with the exponent pattern hoisted into a register by ptxas.
+__device__ __forceinline__ float bits_to_12(uint32_t u) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, 0x007fffff, 0x3f800000, 0xEA;" : "=r"(r) : "r"(u));
+  return __uint_as_float(r);
+}
 // uniform on [0, 1) with 2^-23 spacing
 __device__ __forceinline__ float bits_to_u01(uint32_t u) { return bits_to_12(u) - 1.0f; }
 // uniform on (0, 1] with 2^-23 spacing (safe for log)
@@ -69,12 +74,19 @@ __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ft
 // Box-Muller on two 32-bit words: radius*(cos, sin).  `scale2` multiplies the squared radius, so callers can
 // fold a constant factor (e.g. sigma^2 h) into the square root: r = sqrt(scale2 * (-2 ln u)).
 // 4 MUFU (lg2, sqrt, sin, cos) + 6 FP32 per pair.
+// polar form: radius r = sqrt(neg2ln2_scale2 * log2(u)) with neg2ln2_scale2 = -2 ln2 * scale^2, and (cos, sin)
+__device__ __forceinline__ void box_muller_polar(uint32_t wa, uint32_t wb, float neg2ln2_scale2, float& r, float& c,
+                                                 float& s) {
+  r = fast_sqrt(fast_lg2(bits_to_u01_open0(wa)) * neg2ln2_scale2);
+  const float ang = bits_to_12(wb) * 6.283185307179586f;  // [2pi, 4pi): same law as [0, 2pi)
+  c = fast_cos(ang);
+  s = fast_sin(ang);
+}
 __device__ __forceinline__ void box_muller_scaled(uint32_t wa, uint32_t wb, float scale2, float& n0, float& n1) {
-  const float u = bits_to_u01_open0(wa);
-  const float r = fast_sqrt(fast_lg2(u) * (-1.3862943611198906f * scale2));  // -2 ln2 * scale2 * log2(u)
-  const float ang = bits_to_12(wb) * 6.283185307179586f;                     // [2pi, 4pi): same law as [0, 2pi)
-  n0 = r * fast_cos(ang);
-  n1 = r * fast_sin(ang);
+  float r, c, s;
+  box_muller_polar(wa, wb, -1.3862943611198906f * scale2, r, c, s);
+  n0 = r * c;
+  n1 = r * s;
 }
 __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& n0, float& n1) {
   box_muller_scaled(wa, wb, 1.0f, n0, n1);

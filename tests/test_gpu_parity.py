@@ -71,7 +71,8 @@ def test_estimators_on_injected_noise_vs_reference():
     solver = sm.EulerSolver(sm.Gbm(0.02, 0.3, t(g["x0"]), 1), 3.0, 16, device=DEV)
     po = sm._spec.payoff_struct(sm.EuroCall(1.0), math.exp(-0.06), 1)
     paths, normals, payoffs = solver.solve(bs=256, inject=dict(z=g["z"]), want_payoff=po)
-    assert rel_err(_np(payoffs), g["payoffs"], 1e-2) < RTOL
+    # payoff = D (x - K): the subtraction cancels, so measure against the O(1) scale of the spot
+    assert rel_err(_np(payoffs), g["payoffs"], 1.0) < RTOL
     assert abs(float(payoffs.mean()) - float(g["mean"])) < 1e-6
     assert abs(float(payoffs.std()) / 16.0 - float(g["std"])) < 1e-6
 
@@ -222,7 +223,7 @@ def test_c1_merton_price_vs_series_and_reference_ci(strategy):
         assert abs(s.sample_mean - r["mean"]) <= 1.96 * math.hypot(r["se"], s.sample_std), mode
     # the 'terminal' index (quirk Q1) is visibly biased low, as in the reference
     lo = sm.mc_simple(4 * 10 ** 6, solver, call, csr, bs=10 ** 5, payoff_time='terminal')
-    assert lo.sample_mean < exact - 5e-4
+    assert lo.sample_mean < exact - 2.5 * lo.sample_std
 
 
 @pytest.mark.parametrize("rho", [None, 0.4])
