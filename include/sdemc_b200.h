@@ -125,6 +125,8 @@ typedef struct {
   const float* d_jump_times; /* (n, max_jumps) cumulative jump times, else NULL */
   const float* d_marks;      /* (n, K) raw mark draw per iteration: N(0,1) for LOGNORMAL, U[0,1) for ICDF */
   int32_t K;
+  int32_t total_steps;       /* sdemc_mc_cv only: the batch's total_steps; the reference's compensator sum drops the
+                                interval with index total_steps-1 (varred.py:104,126-127).  0 = drop nothing. */
 } sdemc_inject;
 
 /* fp64 running moments; layout of the device array handed to the kernels (8 doubles). */

@@ -45,7 +45,7 @@ class SdemcRange(C.Structure):
 
 class SdemcInject(C.Structure):
     _fields_ = [("d_z", C.c_void_p), ("d_zc", C.c_void_p), ("d_jump_times", C.c_void_p), ("d_marks", C.c_void_p),
-                ("K", C.c_int32)]
+                ("K", C.c_int32), ("total_steps", C.c_int32)]
 
 
 class SdemcPathsOut(C.Structure):

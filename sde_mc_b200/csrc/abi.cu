@@ -2,6 +2,7 @@
 #include <mutex>
 #include <string>
 
+#include "cv.cuh"
 #include "launch.cuh"
 
 namespace sdemc {
@@ -114,17 +115,98 @@ int sdemc_solve_paths(const sdemc_sde* sde, const sdemc_payoff* payoff, const sd
 
 }  // extern "C"
 
-// ---- not built yet in this revision: explicit, loud status codes (never a silent fallback) ----------------------
 extern "C" {
 
-int sdemc_mlmc_pair(const sdemc_sde*, const sdemc_payoff*, int32_t, int32_t, int32_t, const sdemc_range*,
-                    const sdemc_inject*, sdemc_moments*, void*, void*, void*) {
-  return SDEMC_ERR_UNSUPPORTED;
+int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse, int32_t use_fp64,
+                    const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments, void* d_pair_out,
+                    void* d_workspace, void* stream) {
+  if (!valid_sde(sde) || !range || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
+  if (fine < 1 || coarse < 0) return SDEMC_ERR_BAD_ARG;
+  if (use_fp64) return SDEMC_ERR_UNSUPPORTED;  // fp64 path state: not built (the fp32 pair clamps dt instead of asserting)
+  if (coarse == 0) {
+    // single level (mlmc.py:44-53): the plain fused moments kernel on `fine` steps, payoff at the last state
+    if (inject || d_pair_out || !payoff) return SDEMC_ERR_BAD_ARG;
+    sdemc_sde lvl = *sde;
+    lvl.num_steps = fine;
+    sdemc_payoff po = *payoff;
+    po.index_mode = SDEMC_INDEX_ADAPTED;
+    return solve_common(&lvl, &po, range, nullptr, nullptr, d_moments, d_workspace, stream, false);
+  }
+  if (fine % coarse != 0 || fine == coarse) return SDEMC_ERR_BAD_ARG;
+  if (range->n_paths == 0) return SDEMC_OK;
+  const bool jumps = sde->marks != SDEMC_MARKS_NONE;
+  if (inject) {
+    if (!inject->d_z || inject->K < 1) return SDEMC_ERR_BAD_ARG;
+    if (jumps && (!inject->d_jump_times || !inject->d_marks)) return SDEMC_ERR_BAD_ARG;
+    if (jumps && sde->m == 2 && !inject->d_zc) return SDEMC_ERR_BAD_ARG;
+  }
+  LaunchArgs a;
+  a.sde = to_dev(*sde, fine);
+  a.payoff = to_dev(payoff);
+  a.payoff.index_mode = SDEMC_INDEX_ADAPTED;
+  a.range.path_lo = range->path_lo;
+  a.range.n_paths = range->n_paths;
+  a.keys = make_philox_keys(range->seed);
+  a.inject = to_dev(inject);
+  a.use_inject = inject != nullptr;
+  a.store = false;
+  a.qdepth = 0;
+  a.d_moments = reinterpret_cast<double*>(d_moments);
+  a.d_ws = d_workspace;
+  a.stream = reinterpret_cast<cudaStream_t>(stream);
+  a.out = to_dev(nullptr, 0);
+  return launch_pair(*sde, a, fine, coarse, reinterpret_cast<float*>(d_pair_out));
 }
 
-int sdemc_mc_cv(const sdemc_sde*, const sdemc_payoff*, float, float, const sdemc_mlp*, const sdemc_mlp*,
-                const sdemc_range*, const sdemc_inject*, sdemc_moments*, float*, void*, void*) {
-  return SDEMC_ERR_UNSUPPORTED;
+static bool mlp_ok(const sdemc_mlp* m) {
+  if (!m) return false;
+  for (int i = 0; i < 4; ++i)
+    if (!m->d_w[i] || !m->d_b[i]) return false;
+  return m->in_dim == 2 && m->out_dim == 1 && m->n_hidden_layers == 3 && m->hidden >= 1 && m->hidden <= 63;
+}
+static DevMlp mlp_dev(const sdemc_mlp* m) {
+  DevMlp d;
+  std::memset(&d, 0, sizeof d);
+  if (m) {
+    for (int i = 0; i < 4; ++i) { d.w[i] = m->d_w[i]; d.b[i] = m->d_b[i]; }
+    d.in_dim = m->in_dim; d.hidden = m->hidden; d.out_dim = m->out_dim;
+  }
+  return d;
+}
+
+int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rate, float jump_mean, const sdemc_mlp* f,
+                const sdemc_mlp* g, const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments,
+                float* d_gamma_out, void* d_workspace, void* stream) {
+  if (!valid_sde(sde) || !payoff || !range || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
+  const bool jumps = sde->marks != SDEMC_MARKS_NONE;
+  if (!mlp_ok(f) || (jumps && !mlp_ok(g))) return SDEMC_ERR_UNSUPPORTED;
+  if (range->n_paths == 0) return SDEMC_OK;
+  if (inject) {
+    if (!inject->d_z || inject->K < 1) return SDEMC_ERR_BAD_ARG;
+    if (jumps && (!inject->d_jump_times || !inject->d_marks)) return SDEMC_ERR_BAD_ARG;
+    if (!jumps && inject->K != sde->num_steps) return SDEMC_ERR_BAD_ARG;
+  }
+  LaunchArgs a;
+  a.sde = to_dev(*sde, sde->num_steps);
+  a.payoff = to_dev(payoff);
+  a.payoff.index_mode = SDEMC_INDEX_ADAPTED;
+  a.range.path_lo = range->path_lo;
+  a.range.n_paths = range->n_paths;
+  a.keys = make_philox_keys(range->seed);
+  a.inject = to_dev(inject);
+  a.use_inject = inject != nullptr;
+  a.store = false;
+  a.qdepth = 0;
+  a.d_moments = reinterpret_cast<double*>(d_moments);
+  a.d_ws = d_workspace;
+  a.stream = reinterpret_cast<cudaStream_t>(stream);
+  a.out = to_dev(nullptr, 0);
+  DevCv cv;
+  cv.disc_rate_l2e = (float)((double)disc_rate * 1.4426950408889634);
+  cv.comp_c = (float)(-(double)sde->rate * (double)jump_mean);
+  cv.last_interval = (inject && inject->total_steps > 0) ? inject->total_steps - 1 : 0x7fffffff;
+  cv.gamma_out = d_gamma_out;
+  return launch_cv(*sde, a, mlp_dev(f), mlp_dev(g), cv);
 }
 
 }  // extern "C"

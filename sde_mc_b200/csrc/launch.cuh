@@ -21,5 +21,9 @@ struct LaunchArgs {
 
 int launch_diffusion(const sdemc_sde& s, const LaunchArgs& a);
 int launch_jump(const sdemc_sde& s, const LaunchArgs& a);
+int launch_pair(const sdemc_sde& s, const LaunchArgs& a, int fine, int coarse, float* d_terminal);
+struct DevMlp;
+struct DevCv;
+int launch_cv(const sdemc_sde& s, const LaunchArgs& a, const DevMlp& f, const DevMlp& g, const DevCv& cv);
 
 }  // namespace sdemc

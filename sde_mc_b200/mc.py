@@ -115,7 +115,7 @@ def mc_apply_cvs(models, solver, trials, payoff, discounter, sim_bs=1e5, bs=1000
     are applied with PyTorch on the GPU."""
     start = time.time()
     trials = int(trials)
-    if fused_cv_supported(models, solver, tol):
+    if fused_cv_supported(models, solver, tol) and isinstance(discounter, ConstantShortRate):
         mom = mc_cv_fused(models, solver, trials, payoff, discounter).read()
         mean, stderr = E.mean_and_stderr(mom['sum'], mom['sumsq'], trials)
         return MCStatistics(mean, stderr, time.time() - start, trials)

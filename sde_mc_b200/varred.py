@@ -155,7 +155,7 @@ def apply_adapted_control_variates(models, dl, solver, discounter, tol=0):
 
 
 # ---- fused path: simulation + MLPs + CV sums in one kernel --------------------------------------------------------
-FUSED_CV_ENABLED = False  # flipped on once sdemc_mc_cv is built into the library
+FUSED_CV_ENABLED = True   # set to False to force the stored-trajectory + PyTorch path for every net
 
 
 def _export_mlp(net, dev, keep):
@@ -173,15 +173,21 @@ def _export_mlp(net, dev, keep):
     m.hidden = layers[0][0].shape[0]
     m.out_dim = layers[3][0].shape[0]
     m.n_hidden_layers = 3
-    if layers[1][0].shape != (m.hidden, m.hidden) or layers[2][0].shape != (m.hidden, m.hidden) or m.hidden > 64:
+    if layers[1][0].shape != (m.hidden, m.hidden) or layers[2][0].shape != (m.hidden, m.hidden) or m.hidden > 63:
+        return None
+    if m.in_dim != 2 or m.out_dim != 1:
         return None
     return m
 
 
 def fused_cv_supported(models, solver, tol=0):
     """True when `sdemc_mc_cv` can evaluate these nets: BN-free Linear/ReLU stacks with three equal hidden layers of
-    width <= 64 (the architecture of the experiments, merton_cv_experiment.py:37-38), 1-D 'diag' SDE, tol == 0."""
+    width <= 63 (the architecture of the experiments, merton_cv_experiment.py:37-38), 1-D geometric 'diag' SDE
+    (Gbm, Merton), constant short rate, tol == 0."""
     if tol != 0 or solver.sde.dim != 1 or solver.sde.diffusion_struct != 'diag':
+        return False
+    spec = getattr(solver.sde, 'kernel_spec', None)
+    if spec is None or spec().family != L.FAMILY_GEOMETRIC or spec().asian:
         return False
     if not FUSED_CV_ENABLED:
         return False
@@ -189,7 +195,7 @@ def fused_cv_supported(models, solver, tol=0):
     if len(nets) != (2 if solver.has_jumps else 1):
         return False
     keep = []
-    return all(_export_mlp(n, 'cpu', keep) is not None and n.mlp_layers()[0][0].shape[1] == 2 for n in nets)
+    return all(_export_mlp(n, 'cpu', keep) is not None for n in nets)
 
 
 def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_out=False):
@@ -214,11 +220,11 @@ def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_o
         inj = None
         if inject is not None:
             from .solvers import _as_dev_f32
-            z = _as_dev_f32(inject['z'], dev)
+            z = _as_dev_f32(inject['z'], dev).reshape(trials, -1)
             jt = _as_dev_f32(inject.get('jump_times'), dev)
             mk = _as_dev_f32(inject.get('marks'), dev)
             keep += [z, jt, mk]
-            inj = L.SdemcInject(L.ptr(z), None, L.ptr(jt), L.ptr(mk), int(z.shape[1]))
+            inj = L.SdemcInject(L.ptr(z), None, L.ptr(jt), L.ptr(mk), int(z.shape[1]), int(inject.get('total_steps', 0)))
         rng = L.SdemcRange(int(solver.seed), lo + off, cnt)
         L.check(lib.sdemc_mc_cv(sde, po, float(discounter.r), jm, f, g, rng, inj, L.ptr(mom.buf), L.ptr(gam),
                                 L.ptr(L.workspace(dev)), L.stream_ptr(dev)))

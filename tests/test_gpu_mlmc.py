@@ -1,0 +1,115 @@
+"""GPU tests of the fused MLMC pair kernels (H4, H11, E4): injected-noise parity against the golden vectors of the
+reference's fp64 run and against the fp32 oracle, then statistical acceptance of mc_multilevel (C5)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from common import MLMC_CASES, golden, golden_json, mlmc_levels, oracle, oracle_sde, rel_err, sm, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _np(x):
+    return x.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", sorted(MLMC_CASES))
+def test_jump_pair_vs_reference_golden(name):
+    """fp32 kernel vs the reference's fp64 coupled pair on the same (float-representable) noise: 2e-5 relative"""
+    g = golden(name)
+    fine, coarse = mlmc_levels(name)
+    solver = sm.JumpEulerSolver(MLMC_CASES[name](g), float(g["T"]), fine, device=DEV,
+                                exact_jumps=bool(int(g["exact_jumps"])))
+    inject = dict(z=g["z"].astype(np.float32), jump_times=g["jump_times"].astype(np.float32),
+                  marks=g["marks"].astype(np.float32))
+    if "zc" in g.files:
+        inject["zc"] = g["zc"].astype(np.float32)
+    (pf, pc), _ = solver.multilevel_solve(g["z"].shape[0], (fine, coarse), inject=inject)
+    # the oracle in fp32 on the SAME rounded inputs is the tight check ...
+    fl, cl, iters, total = oracle.jump_pair(oracle_sde(solver, fine), fine, coarse, inject["z"], inject.get("zc"),
+                                            inject["jump_times"], inject["marks"], np.float32)
+    assert total > 0
+    assert rel_err(_np(pf)[:, -1], fl) < 1e-5
+    assert rel_err(_np(pc)[:, -1], cl) < 1e-5
+    # ... and the reference's own fp64 run bounds the fp32 rounding of the whole pair
+    assert rel_err(_np(pf)[:, -1], g["fine_last"]) < 5e-5
+    assert rel_err(_np(pc)[:, -1], g["coarse_last"]) < 5e-5
+
+
+def test_diffusion_pair_vs_reference_golden():
+    g = golden("diff_gbm_mlmc_8_2")
+    solver = sm.EulerSolver(sm.Gbm(0.02, 0.3, t(g["x0"]), 1), float(g["T"]), 8, device=DEV)
+    (pf, pc), _ = solver.multilevel_solve(16, (8, 2), inject=dict(z=g["z"]))
+    assert rel_err(_np(pf)[:, -1], g["paths_fine"][:, -1]) < 1e-5
+    assert rel_err(_np(pc)[:, -1], g["paths_coarse"][:, -1]) < 1e-5
+
+
+def test_pair_large_inject_vs_oracle():
+    rng = np.random.default_rng(5)
+    bs, fine, coarse = 4096, 16, 4
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    solver = sm.JumpEulerSolver(sde, 3, fine, device=DEV)
+    K = coarse + solver.max_jumps
+    z = rng.standard_normal((bs, K * 4, 1)).astype(np.float32)
+    jt = np.cumsum(rng.exponential(1.0, (bs, solver.max_jumps)), axis=1).astype(np.float32)
+    mk = rng.standard_normal((bs, K)).astype(np.float32)
+    fl, cl, iters, total = oracle.jump_pair(oracle_sde(solver, fine), fine, coarse, z, None, jt, mk, np.float32)
+    (pf, pc), _ = solver.multilevel_solve(bs, (fine, coarse), inject=dict(z=z, jump_times=jt, marks=mk))
+    assert rel_err(_np(pf)[:, -1], fl) < 1e-5 and rel_err(_np(pc)[:, -1], cl) < 1e-5
+
+
+def test_level_variances_match_reference_pilot():
+    """per-level Var[P_l - P_{l-1}] against the reference's fp64 pilot (40000 pairs per level)"""
+    ref = golden_json("ref_stats")["c5_level_vars_n40000"]
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    solver = sm.JumpEulerSolver(sde, 3, 1, device=DEV)
+    levels = [1, 2, 4, 8, 16, 32, 64, 128]
+    call, csr = sm.EuroCall(1.0), sm.ConstantShortRate(0.02)
+    n = 400000
+    from sde_mc_b200.mlmc import _level_moments
+    for i, lv in enumerate(levels):
+        m = _level_moments(solver, call, csr, n, lv, levels[i - 1] if i else 0).read()
+        var = (m["sumsq"] - m["sum"] ** 2 / n) / (n - 1)
+        # sample variance of a heavy-ish tailed difference at n=40000: allow 15 %
+        assert abs(var - ref[i]) < 0.15 * ref[i], (lv, var, ref[i])
+
+
+def test_mc_multilevel_c5():
+    """C5.  With exact_jumps=False the reference's coupled pair applies the jump to the state before the LAST fine
+    sub-step (solvers.py:275,296-299), which is the post-step state whenever the jump time is reached early; its
+    fine path then has a different law from the same level run as a coarse path, the telescoping sum no longer
+    cancels and the estimate sits ~1.4e-3 below the Merton series (the reference's own fp64 run shows it too).
+    We reproduce the reference: exact_jumps=False is checked against the reference's CI, exact_jumps=True (the
+    LevyRainbowMLMC setting, where the telescoping is exact) against the closed form."""
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    levels = [1, 2, 4, 8, 16, 32, 64, 128]
+    call, csr = sm.EuroCall(1.0), sm.ConstantShortRate(0.02)
+    exact = sm.merton_call(1, 1, 3, 0.02, 0.2, -0.05, 0.3, 1)
+    ref = golden_json("ref_stats")["c5_mlmc_eps2e-3"]
+
+    solver = sm.JumpEulerSolver(sde, 3, 1, device=DEV)
+    trials = sm.get_optimal_trials(10 ** 5, levels, 2e-4, solver, call, csr)
+    assert len(trials) == len(levels) and all(a >= b for a, b in zip(trials, trials[1:]))
+    for ours, theirs in zip(trials, ref["trials"]):   # allocation scales like eps^-2: 100x the reference's at 2e-3
+        assert 0.6 < ours / (100.0 * theirs) < 1.6, (ours, theirs)
+    st = sm.mc_multilevel(trials, levels, solver, call, csr)
+    assert st.sample_std * 1.96 < 2.3e-4
+    assert abs(st.sample_mean - ref["mean"]) <= 1.96 * math.hypot(ref["se"], st.sample_std)
+    assert st.sample_mean < exact - 5e-4              # the reference's telescoping bias is reproduced, not hidden
+
+    solver = sm.JumpEulerSolver(sde, 3, 1, device=DEV, exact_jumps=True)
+    trials = sm.get_optimal_trials(10 ** 5, levels, 2e-4, solver, call, csr)
+    st = sm.mc_multilevel(trials, levels, solver, call, csr)
+    assert st.sample_std * 1.96 < 2.3e-4
+    assert abs(st.sample_mean - exact) <= 1.96 * st.sample_std + 3e-4     # + level-7 discretisation bias
+
+
+def test_mc_multilevel_works_for_diffusions_too():
+    """the reference raises TypeError here (no low_storage on DiffusionSolver); ours runs the uniform-grid pair"""
+    p = sm.BlackScholesEuroCall.default_params(1, DEV)
+    levels = [2, 8, 32, 128]
+    st = sm.mc_multilevel([2 * 10 ** 6, 4 * 10 ** 5, 10 ** 5, 3 * 10 ** 4], levels, p.solver, p.payoff, p.discounter)
+    assert abs(st.sample_mean - sm.bs_call(1, 1, 3, 0.02, 0.3)) <= 1.96 * st.sample_std + 3e-4
