@@ -27,12 +27,19 @@ sys.path.insert(0, ROOT)
 
 # canonical algorithmic work per nominal path-step, in FP32/ALU/XU lane-operations (SURVEY.md section 8d,
 # restated in DESIGN.md): one N(0,1) = 21 ops; GBM Euler step 2 ops; Merton jump-adapted iteration 39 ops x 1.03.
-OPS_PER_PATH_STEP = {"gbm": 23.0, "merton": 40.0}
+OPS_PER_PATH_STEP = {"gbm": 23.0, "merton": 40.0, "levy2d": 240.0, "merton_cv": 40.0}
 WORKLOADS = {
+    # BASELINE.json configs[1]
     "gbm": dict(name="gbm_1d_eurocall_euler_1e9x252", num_steps=252, paths=10 ** 9, cpu_paths=10 ** 5),
+    # configs[0] at the size the north-star target is quoted on
     "merton": dict(name="merton_1d_eurocall_jump_adapted_euler_1e9x100", num_steps=100, paths=10 ** 9,
                    cpu_paths=10 ** 5),
+    # configs[3]: 2-D Levy-driven rainbow, 1e8 paths x 256 steps
+    "levy2d": dict(name="levy_2d_rainbow_jump_adapted_euler_1e8x256", num_steps=256, paths=10 ** 8, cpu_paths=5000),
+    # configs[2]: Merton 1-D with the neural control variate applied in-kernel (tcgen05), 1e8 paths x 200 steps
+    "merton_cv": dict(name="merton_1d_neural_cv_tcgen05_1e8x200", num_steps=200, paths=10 ** 8, cpu_paths=10 ** 4),
 }
+CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 
 
 def parse():
@@ -51,9 +58,19 @@ def build_problem(sm, workload, device):
     import torch
     if workload == "gbm":
         p = sm.BlackScholesEuroCall.default_params(252, device)
-        return p.solver, p.payoff, p.discounter, "terminal"
+        return p.solver, p.payoff, p.discounter, "terminal", None
+    if workload == "levy2d":
+        levy = sm.ExpExampleLevy(1, 1, 0.5, 2, 0.02, 0.3, 0.2, 0.001, dim=2)
+        sde = sm.LevySde(levy, torch.tensor([1., 1.]))
+        return sm.JumpEulerSolver(sde, 3, 256, device=device), sm.Rainbow(1.0), sm.ConstantShortRate(0.02), "adapted", None
     sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
-    return (sm.JumpEulerSolver(sde, 3, 100, device=device), sm.EuroCall(1.0), sm.ConstantShortRate(0.02), "adapted")
+    if workload == "merton_cv":
+        torch.manual_seed(0)   # random-init weights of the experiments' architecture (no checkpoints offline)
+        nets = [sm.Mlp(2, [50, 50, 50], 1, batch_norm=False, batch_norm_init=False, device=device).eval()
+                for _ in range(2)]
+        return (sm.JumpEulerSolver(sde, 3, 200, device=device), sm.EuroCall(1.0), sm.ConstantShortRate(0.02),
+                "adapted", nets)
+    return (sm.JumpEulerSolver(sde, 3, 100, device=device), sm.EuroCall(1.0), sm.ConstantShortRate(0.02), "adapted", None)
 
 
 class ClockSampler(threading.Thread):
@@ -107,6 +124,15 @@ def cpu_reference(workload, steps, warmup, sample_paths=None):
     if workload == "gbm":
         spec = sm.Gbm(0.02, 0.3, torch.tensor([1.]), 1).kernel_spec()
         run = lambda: tp.mc_simple_batched(spec, 3, 252, n, n, tp.payoff_call_on("euro_call", 1.0), 0.02, False, "terminal")
+    elif workload == "levy2d":
+        levy = sm.ExpExampleLevy(1, 1, 0.5, 2, 0.02, 0.3, 0.2, 0.001, dim=2)
+        spec = sm.LevySde(levy, torch.tensor([1., 1.])).kernel_spec()
+        run = lambda: tp.mc_simple_batched(spec, 3, 256, n, n, tp.payoff_call_on("rainbow", 1.0), 0.02, True, "adapted")
+    elif workload == "merton_cv":
+        spec = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1).kernel_spec()
+        torch.manual_seed(0)
+        nets = [sm.Mlp(2, [50, 50, 50], 1, batch_norm=False, batch_norm_init=False).eval() for _ in range(2)]
+        run = lambda: tp.mc_apply_cvs_batched(spec, 3, 200, n, nets, 0.02, tp.payoff_call_on("euro_call", 1.0), 1000)
     else:
         spec = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1).kernel_spec()
         run = lambda: tp.mc_simple_batched(spec, 3, 100, n, n, tp.payoff_call_on("euro_call", 1.0), 0.02, True, "adapted")
@@ -162,7 +188,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L.load()
     paths = int(args.paths or w["paths"])
-    solver, payoff, discounter, payoff_time = build_problem(sm, args.workload, dev)
+    solver, payoff, discounter, payoff_time, nets = build_problem(sm, args.workload, dev)
     index_mode = L.INDEX_ADAPTED if payoff_time == "adapted" else L.INDEX_TERMINAL
 
     def barrier():
@@ -173,6 +199,8 @@ def main():
     # ---- device-resident leg: inputs (a parameter struct + Philox key) are already on the device side ----
     def device_step():
         # every rank: `paths` paths of its own global path-id range (weak scaling), then the 64-byte all-reduce
+        if nets is not None:
+            return sm.mc_cv_fused(nets, solver, paths * world, payoff, discounter)
         return E.run_moments(solver, payoff, discounter, paths * world, index_mode)
 
     for _ in range(args.warmup):
@@ -199,7 +227,10 @@ def main():
     t0 = time.perf_counter()
     stats = None
     for _ in range(args.steps):
-        stats = sm.mc_simple(paths * world, solver, payoff, discounter, bs=10 ** 6, payoff_time=payoff_time)
+        if nets is not None:
+            stats = sm.mc_apply_cvs(nets, solver, paths * world, payoff, discounter, sim_bs=10 ** 5, bs=2000)
+        else:
+            stats = sm.mc_simple(paths * world, solver, payoff, discounter, bs=10 ** 6, payoff_time=payoff_time)
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3
     if rank == 0:
@@ -234,7 +265,8 @@ def main():
                        "parallelism": "paths sharded over %d GPU(s), one 64-byte all-reduce per step" % world},
             "e2e": {"value": e2e, "unit": "path-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 64,
                     "ms_per_step": e2e_ms / args.steps,
-                    "call": "sde_mc_b200.mc_simple(paths, solver, payoff, discounter, bs=1e6)"},
+                    "call": ("sde_mc_b200.mc_apply_cvs([f, g], solver, paths, payoff, discounter)" if nets is not None
+                             else "sde_mc_b200.mc_simple(paths, solver, payoff, discounter, bs=1e6)")},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak, "unit": "Tlaneop/s",
@@ -244,8 +276,22 @@ def main():
                                      % (sm_count, mhz),
                          "executed_iterations_per_path": result["iters"] / result["n"]},
             "estimate": {"mean": mean, "stderr": se, "n": n_total,
-                         "closed_form": 0.22943206 if args.workload == "gbm" else 0.26298121},
+                         "closed_form": {"gbm": 0.22943206, "levy2d": None}.get(args.workload, 0.26298121)},
         }
+        if nets is not None:
+            iters_per_s = result["iters"] / (dev_ms * 1e-3) * args.steps / world
+            tf = CV_TENSOR_FLOP_PER_ITER * iters_per_s / 1e12
+            peaks = {}
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                    peaks = json.load(fh)
+            except OSError:
+                pass
+            tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+            out["roofline_tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
+                                      "frac": tf / tpeak, "traffic": None,
+                                      "flop_per_path_iteration": CV_TENSOR_FLOP_PER_ITER,
+                                      "peak_def": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF"}
         if world == 1 and not args.no_cpu_baseline:
             _, _, info = cpu_reference(args.workload, 2, 1)
             out["cpu_baseline"] = info

@@ -182,3 +182,48 @@ def mc_simple_batched(spec, T, num_steps, num_trials, bs, payoff, rate_r, jumps,
     mean = s1 / num_trials
     sd = torch.sqrt((s2 / num_trials - mean ** 2) * (num_trials / (num_trials - 1))) / math.sqrt(num_trials)
     return float(mean), float(sd), time.time() - start
+
+
+def apply_adapted_cvs(f, g, out, aux, payoffs, rate, jump_mean, r, bs):
+    """apply_adapted_control_variates varred.py:98-131 over stored jump-adapted paths, in NN batches of `bs` rows
+    like the reference's DataLoader (AdaptedPathData drops the last time index, nets.py:192-200)."""
+    normals, time_paths, left, total, jump_paths = aux
+    n = out.shape[0]
+    paths, left, times, jumps, normals = out[:, :total], left[:, :total], time_paths[:, :total], \
+        jump_paths[:, :total], normals[:, :total]
+    s1, s2 = 0.0, 0.0
+    with torch.inference_mode():
+        for lo in range(0, n, bs):
+            sl = slice(lo, min(lo + bs, n))
+            b, S, d = paths[sl].shape
+            tt = times[sl]
+            h = torch.diff(tt, dim=1)
+            disc = torch.exp(-tt * r)
+            f_out = f(torch.cat([tt.reshape(b * S, 1), paths[sl].reshape(b * S, d)], dim=-1)).view(normals[sl].shape)
+            bcv = (normals[sl] * f_out * disc).sum(-1).sum(-1)
+            g_out = g(torch.cat([tt.reshape(b * S, 1), left[sl].reshape(b * S, d)], dim=-1)).view(b, S, d)
+            jcv = (g_out * disc * jumps[sl]).sum(-1).sum(-1)
+            comp = (-rate * jump_mean * g_out[:, :-1] * disc[:, :-1] * h).sum(-1).sum(-1)
+            gam = payoffs[sl] + bcv + jcv + comp
+            s1 += gam.sum()
+            s2 += (gam * gam).sum()
+    return s1, s2
+
+
+def mc_apply_cvs_batched(spec, T, num_steps, num_trials, nets, rate_r, payoff, nn_bs, sim_bs=10 ** 5):
+    """mc_apply_cvs mc.py:195-242 for a jump SDE: simulate with full storage, apply (f, g), running sums."""
+    f, g = nets
+    df = torch.exp(-torch.tensor(float(T)) * rate_r)
+    remaining, s1, s2 = int(num_trials), 0.0, 0.0
+    start = time.time()
+    while remaining > 0:
+        batch = min(int(sim_bs), remaining)
+        remaining -= batch
+        out, aux = jump_solve(spec, T, num_steps, batch, low_storage=False)
+        pay = payoff(out[:, aux[3]]) * df
+        a, b = apply_adapted_cvs(f, g, out, aux, pay, float(spec.rate), float(spec.jump_mean), rate_r, nn_bs)
+        s1 += a
+        s2 += b
+    mean = s1 / num_trials
+    var = (s2 - s1 * s1 / num_trials) / (num_trials - 1)
+    return float(mean), float(var.sqrt() / math.sqrt(num_trials)), time.time() - start

@@ -10,6 +10,7 @@ from abc import ABC, abstractmethod
 
 import numpy as np
 import torch
+import torch.nn.functional as F  # noqa: F401  (star-exported by the reference's solvers.py:2)
 from scipy.stats import poisson
 
 from . import _lib as L

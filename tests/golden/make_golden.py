@@ -496,8 +496,32 @@ def seeded_cases():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["diffusion", "jump", "mlmc", "payoff", "cv", "estimator", "seeded"]
+    which = [a for a in sys.argv[1:] if a != "api"] or ([] if "api" in sys.argv[1:] else
+                                                          ["diffusion", "jump", "mlmc", "payoff", "cv", "estimator", "seeded"])
     torch.manual_seed(0)
     for w in which:
         {"diffusion": diffusion_cases, "jump": jump_cases, "mlmc": mlmc_cases, "payoff": payoff_cases,
          "cv": cv_cases, "estimator": estimator_cases, "seeded": seeded_cases}[w]()
+
+
+def api_names():
+    """public names of the reference's star-exported namespace (the drop-in must offer every one of them)"""
+    names = sorted(n for n in dir(ref) if not n.startswith("_"))
+    sigs = {}
+    import inspect
+    for n in names:
+        obj = getattr(ref, n)
+        if inspect.isclass(obj) and obj.__module__.startswith("sde_mc"):
+            try:
+                sigs[n] = list(inspect.signature(obj.__init__).parameters)
+            except (TypeError, ValueError):
+                pass
+        elif inspect.isfunction(obj) and obj.__module__.startswith("sde_mc"):
+            sigs[n] = list(inspect.signature(obj).parameters)
+    with open(os.path.join(HERE, "api_names.json"), "w") as fh:
+        json.dump({"names": names, "signatures": sigs}, fh, indent=1)
+    print("wrote api_names.json", len(names), len(sigs))
+
+
+if __name__ == "__main__" and "api" in sys.argv[1:]:
+    api_names()
