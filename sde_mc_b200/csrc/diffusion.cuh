@@ -7,15 +7,18 @@ namespace sdemc {
 // One thread per path, grid-stride over the call's path range.
 //   INJECT : unit normals come from DevInject.z (deterministic parity mode) instead of Philox
 //   STORE  : write the solve() outputs (paths, normals, payoffs); otherwise accumulate moments only
+#ifndef SDEMC_DIFF_MIN_BLOCKS
+#define SDEMC_DIFF_MIN_BLOCKS 1
+#endif
 template <class C, bool HESTON, bool INJECT, bool STORE>
-__global__ void __launch_bounds__(256) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+__global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BLOCKS) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                         const PhiloxKeys keys, const DevInject inj, const DevOut out,
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
   constexpr int DIM = C::DIM, M = C::M, BASE = C::BASE;
-  constexpr int NZ = BASE * M;            // normals consumed per step
-  constexpr int NZP = pad_pow2(NZ);       // padded to a divisor / multiple of the 4-word Philox block
-  constexpr int SPB = NZP <= 4 ? 4 / NZP : 1;  // steps served by one group of blocks
-  constexpr int BPS = NZP <= 4 ? 1 : NZP / 4;  // Philox blocks per group
+  constexpr int NZ = BASE * M;                  // normals consumed per step
+  constexpr int SPB = steps_per_group(NZ);      // steps served by one group of Philox blocks (6 normals per block)
+  constexpr int BPS = blocks_per_group(NZ);     // Philox blocks per group
+  constexpr int NBUF = BPS * kNormalsPerBlock;
   constexpr bool FAST1D = DIM == 1 && M == 1 && !HESTON && !INJECT && !STORE;
   const int S = s.num_steps;
 
@@ -36,38 +39,36 @@ __global__ void __launch_bounds__(256) diffusion_kernel(const DevSde s, const De
     int b_first = 0;
     if constexpr (FAST1D) {
       // 1-D single-driver moments path (GBM / log-GBM): sigma sqrt(h) is folded into the Box-Muller radius and
-      // full Philox blocks (4 steps) run without per-step predicates: 2 FFMA per step on top of the normal.
-      const int nb_full = S >> 2;
+      // full Philox blocks (6 steps) run without per-step predicates: 2 FFMA per step on top of the normal.
+      const int nb_full = S / SPB;
       for (int b = 0; b < nb_full; ++b) {
         uint32_t o[4];
         philox4x32_10((uint32_t)b, STREAM_DIFFUSION, plo, phi, keys, o);
-        float r0, c0, s0, r1, c1, s1;
-        box_muller_polar(o[0], o[1], s.neg2ln2_b1s2, r0, c0, s0);
-        box_muller_polar(o[2], o[3], s.neg2ln2_b1s2, r1, c1, s1);
-        const float g0 = fmaf(r0, c0, s.ah[0]), g1 = fmaf(r0, s0, s.ah[0]);
-        const float g2 = fmaf(r1, c1, s.ah[0]), g3 = fmaf(r1, s1, s.ah[0]);
-        if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
-          x[0] = fmaf(x[0], g0, x[0]);
-          x[0] = fmaf(x[0], g1, x[0]);
-          x[0] = fmaf(x[0], g2, x[0]);
-          x[0] = fmaf(x[0], g3, x[0]);
-        } else {
-          x[0] += (g0 + g1) + (g2 + g3);
+        float r[3], c[3], sn[3];
+        philox_polar3(o, s.neg2ln2_b1s2, r, c, sn);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float g0 = fmaf(r[j], c[j], s.ah[0]), g1 = fmaf(r[j], sn[j], s.ah[0]);
+          if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
+            x[0] = fmaf(x[0], g0, x[0]);
+            x[0] = fmaf(x[0], g1, x[0]);
+          } else {
+            x[0] += g0 + g1;
+          }
         }
       }
-      b_first = nb_full;  // the generic loop below finishes the S % 4 remaining steps
+      b_first = nb_full;  // the generic loop below finishes the S % 6 remaining steps
     }
 
     for (int b = b_first; b * SPB < S; ++b) {
-      float nrm[SPB * NZP];
+      float nrm[NBUF];
       float extra[SPB];  // injected normal of the asian integral component (recorded, never used)
       if (!INJECT) {
 #pragma unroll
         for (int r = 0; r < BPS; ++r) {
           uint32_t o[4];
           philox4x32_10((uint32_t)(b * BPS + r), STREAM_DIFFUSION, plo, phi, keys, o);
-          box_muller(o[0], o[1], nrm[4 * r + 0], nrm[4 * r + 1]);
-          box_muller(o[2], o[3], nrm[4 * r + 2], nrm[4 * r + 3]);
+          philox_normals6(o, nrm + kNormalsPerBlock * r);
         }
 #pragma unroll
         for (int sp = 0; sp < SPB; ++sp) extra[sp] = 0.0f;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) diffusion_kernel(const DevSde s, const De
           if (step < S) {
             const float* zp = inj.z + (i * (uint64_t)S + step) * (DIM * M);
 #pragma unroll
-            for (int q = 0; q < NZ; ++q) nrm[sp * NZP + q] = zp[q];
+            for (int q = 0; q < NZ; ++q) nrm[sp * NZ + q] = zp[q];
             if (C::ASIAN) extra[sp] = zp[BASE * M];
           }
         }
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(256) diffusion_kernel(const DevSde s, const De
           float z1[kMaxDim], z2[kMaxDim], w1[kMaxDim], w2[kMaxDim];
 #pragma unroll
           for (int k = 0; k < BASE; ++k) {
-            z1[k] = nrm[sp * NZP + k * M];
-            z2[k] = M == 2 ? nrm[sp * NZP + k * M + 1] : 0.0f;
+            z1[k] = nrm[sp * NZ + k * M];
+            z2[k] = M == 2 ? nrm[sp * NZ + k * M + 1] : 0.0f;
           }
           correlate<C>(s, z1, w1);
           if (M == 2) correlate<C>(s, z2, w2);  // DiffusionSolver: every driver is a correlated dim-vector (:79-81)

@@ -73,7 +73,10 @@ struct Cfg {
   static constexpr int BASE = ASIAN_ ? DIM_ - 1 : DIM_;  // components driven by noise
 };
 
-constexpr int pad_pow2(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : 8; }
+// How a stream of NZ normals per step maps onto Philox blocks of 6 normals: NZ in {1,2,3} -> 6/NZ steps share a
+// block; larger NZ -> ceil(NZ/6) blocks per step (slots beyond NZ unused).
+constexpr int steps_per_group(int nz) { return nz <= 3 ? kNormalsPerBlock / nz : 1; }
+constexpr int blocks_per_group(int nz) { return nz <= 3 ? 1 : (nz + kNormalsPerBlock - 1) / kNormalsPerBlock; }
 
 // ------------------------------------------------------------------------------------------------------------
 // marks

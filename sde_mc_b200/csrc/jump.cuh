@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
                                                    void* __restrict__ d_ws) {
   constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M, MARKS = C::MARKS;
   constexpr int NZ = BASE + (M == 2 ? 1 : 0);  // normals per iteration
-  constexpr int NZP = pad_pow2(NZ);
-  constexpr int SPB = NZP <= 4 ? 4 / NZP : 1;
-  constexpr int BPS = NZP <= 4 ? 1 : NZP / 4;
+  constexpr int SPB = steps_per_group(NZ);     // iterations served by one group of Philox blocks (6 normals each)
+  constexpr int BPS = blocks_per_group(NZ);
+  constexpr int NBUF = BPS * kNormalsPerBlock;
   constexpr bool INJECT = JSRC == JSRC_INJECT;
   using Src = typename std::conditional<JSRC == JSRC_INJECT, InjectJumps<MARKS>,
                                         typename std::conditional<JSRC == JSRC_QUEUE, QueueJumps<MARKS>,
@@ -278,14 +278,13 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
     else src.init(plo, phi);
 
     // fetch the unit normals of SPB consecutive iterations starting at iteration b * SPB
-    auto load_normals = [&](int b, float(&nrm)[SPB * NZP], float(&extra)[SPB]) {
+    auto load_normals = [&](int b, float(&nrm)[NBUF], float(&extra)[SPB]) {
       if (!INJECT) {
 #pragma unroll
         for (int r = 0; r < BPS; ++r) {
           uint32_t o[4];
           philox4x32_10((uint32_t)(b * BPS + r), STREAM_DIFFUSION, plo, phi, keys, o);
-          box_muller(o[0], o[1], nrm[4 * r + 0], nrm[4 * r + 1]);
-          box_muller(o[2], o[3], nrm[4 * r + 2], nrm[4 * r + 3]);
+          philox_normals6(o, nrm + kNormalsPerBlock * r);
         }
 #pragma unroll
         for (int sp = 0; sp < SPB; ++sp) extra[sp] = 0.0f;
@@ -295,13 +294,13 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
           const int k = b * SPB + sp;
           extra[sp] = 0.0f;
 #pragma unroll
-          for (int q = 0; q < NZP; ++q) nrm[sp * NZP + q] = 0.0f;
+          for (int q = 0; q < NZ; ++q) nrm[sp * NZ + q] = 0.0f;
           if (k < inj.K) {
             const float* zp = inj.z + (i * (uint64_t)inj.K + k) * DIM;
 #pragma unroll
-            for (int q = 0; q < BASE; ++q) nrm[sp * NZP + q] = zp[q];
+            for (int q = 0; q < BASE; ++q) nrm[sp * NZ + q] = zp[q];
             if (C::ASIAN) extra[sp] = zp[BASE];
-            if (M == 2) nrm[sp * NZP + BASE] = inj.zc[i * (uint64_t)inj.K + k];
+            if (M == 2) nrm[sp * NZ + BASE] = inj.zc[i * (uint64_t)inj.K + k];
           }
         }
       }
@@ -328,13 +327,13 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
       for (int b = 0; b * SPB < out.S; ++b) {
-        float nrm[SPB * NZP], extra[SPB];
+        float nrm[NBUF], extra[SPB];
         load_normals(b, nrm, extra);
 #pragma unroll
         for (int sp = 0; sp < SPB; ++sp) {
           if (st.k < out.S) {
             if (st.t < s.T) own_iters = st.k + 1;
-            jump_iteration<C, Src, true>(s, keys, st, src, nrm + sp * NZP, out, i, extra[sp]);
+            jump_iteration<C, Src, true>(s, keys, st, src, nrm + sp * NZ, out, i, extra[sp]);
             if (st.k == n) {
 #pragma unroll
               for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
@@ -347,35 +346,32 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
       // so full Philox blocks run without the loop-exit test.
       const int nb_full = n / SPB;
       for (int b = 0; b < nb_full; ++b) {
-        float nrm[SPB * NZP], extra[SPB];
+        float nrm[NBUF], extra[SPB];
         load_normals(b, nrm, extra);
 #pragma unroll
-        for (int sp = 0; sp < SPB; ++sp) jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZP, out, i, 0.0f);
+        for (int sp = 0; sp < SPB; ++sp) jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZ, out, i, 0.0f);
       }
       if (st.k == n) {
 #pragma unroll
         for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
       }
-      // phase 2: the few remaining iterations (those forced by jumps), one per trip with the exit test.  The
-      // iteration's Philox block is regenerated and its lane selected, so the stream stays identical to STORE mode.
+      // phase 2: the few remaining iterations (those forced by jumps) with the exit test; same block structure, so
+      // the Philox stream stays identical to STORE mode.
       const int kcap = INJECT ? inj.K : 4 * (n + s.max_jumps) + 64;
-      while (st.t < s.T && st.k < kcap) {
-        float nrm[SPB * NZP], extra[SPB], zn[NZP];
-        load_normals(st.k / SPB, nrm, extra);
-        const int sp_dyn = st.k % SPB;
+      bool done = !(st.t < s.T) || st.k >= kcap;
+      for (int b = nb_full; !done; ++b) {
+        float nrm[NBUF], extra[SPB];
+        load_normals(b, nrm, extra);
 #pragma unroll
-        for (int q = 0; q < NZP; ++q) zn[q] = nrm[q];
+        for (int sp = 0; sp < SPB; ++sp) {
+          if (!done) {
+            jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZ, out, i, 0.0f);
+            if (st.k == n) {
 #pragma unroll
-        for (int sp = 1; sp < SPB; ++sp) {
-          if (sp == sp_dyn) {
-#pragma unroll
-            for (int q = 0; q < NZP; ++q) zn[q] = nrm[sp * NZP + q];
+              for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
+            }
+            done = !(st.t < s.T) || st.k >= kcap;
           }
-        }
-        jump_iteration<C, Src, false>(s, keys, st, src, zn, out, i, 0.0f);
-        if (st.k == n) {
-#pragma unroll
-          for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
         }
       }
       own_iters = st.k;

@@ -92,6 +92,43 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& n0, 
   box_muller_scaled(wa, wb, 1.0f, n0, n1);
 }
 
+// Six normals from ONE Philox block.  IMAD.WIDE runs at quarter rate on sm_100 (measured: 20 of them = 80 of the 83
+// SMSP-cycles a Philox4x32-10 block costs), so the 128 bits are spent frugally: three Box-Muller pairs, each with a
+// 23-bit radius uniform (low bits of o0, o1, o2: tail reach 5.6 sigma, variance deficit 2e-6) and a 16-bit angle
+// (o3 low half, o3 high half, top bytes of o0 and o1: 65536 directions).  Polar form so callers can fold a scale
+// into the radius: r = sqrt(neg2ln2_scale2 * log2 u), unit normals are r*c and r*s.
+__device__ __forceinline__ float angle_bits_to_12(uint32_t k16_in_low_bits) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, 0x0000ffff, 0x3f800000, 0xEA;" : "=r"(r) : "r"(k16_in_low_bits));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void philox_polar3(const uint32_t (&o)[4], float neg2ln2_scale2, float (&r)[3],
+                                              float (&c)[3], float (&s)[3]) {
+  const float f0 = angle_bits_to_12(o[3]);
+  const float f1 = __uint_as_float((o[3] >> 16) | 0x3f800000u);
+  const float f2 = angle_bits_to_12(__byte_perm(o[0], o[1], 0x0073));  // bytes {o0[31:24], o1[31:24]}
+  const float fa[3] = {f0, f1, f2};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    r[j] = fast_sqrt(fast_lg2(bits_to_u01_open0(o[j])) * neg2ln2_scale2);
+    // f in [1, 1 + 2^-7): (f - 1) * 128 * 2pi is the angle in [0, 2pi)
+    const float ang = fmaf(fa[j], 804.247719318987f, -804.247719318987f);
+    c[j] = fast_cos(ang);
+    s[j] = fast_sin(ang);
+  }
+}
+// six unit normals in slot order (r0 c0, r0 s0, r1 c1, r1 s1, r2 c2, r2 s2)
+__device__ __forceinline__ void philox_normals6(const uint32_t (&o)[4], float* n) {
+  float r[3], c[3], s[3];
+  philox_polar3(o, -1.3862943611198906f, r, c, s);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    n[2 * j] = r[j] * c[j];
+    n[2 * j + 1] = r[j] * s[j];
+  }
+}
+constexpr int kNormalsPerBlock = 6;
+
 // Exp(1) draw from one word: -ln(u), u in (0,1]
 __device__ __forceinline__ float exp1_from_bits(uint32_t w) { return fast_lg2(bits_to_u01_open0(w)) * -0.6931471805599453f; }
 
