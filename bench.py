@@ -39,6 +39,13 @@ WORKLOADS = {
     # configs[2]: Merton 1-D with the neural control variate applied in-kernel (tcgen05), 1e8 paths x 200 steps
     "merton_cv": dict(name="merton_1d_neural_cv_tcgen05_1e8x200", num_steps=200, paths=10 ** 8, cpu_paths=10 ** 4),
 }
+WORKLOADS.update({
+    # path-storing mode (the solve() contract): HBM-write-bound; bytes per path = reference layouts
+    "gbm_store": dict(name="gbm_1d_solve_store_paths_4e6x252", num_steps=252, paths=4 * 10 ** 6, cpu_paths=10 ** 5),
+    "merton_store": dict(name="merton_1d_solve_full_storage_2e6x100", num_steps=100, paths=2 * 10 ** 6,
+                         cpu_paths=10 ** 5),
+})
+OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0})
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 
 
@@ -56,7 +63,7 @@ def parse():
 
 def build_problem(sm, workload, device):
     import torch
-    if workload == "gbm":
+    if workload in ("gbm", "gbm_store"):
         p = sm.BlackScholesEuroCall.default_params(252, device)
         return p.solver, p.payoff, p.discounter, "terminal", None
     if workload == "levy2d":
@@ -121,7 +128,13 @@ def cpu_reference(workload, steps, warmup, sample_paths=None):
     w = WORKLOADS[workload]
     n = int(sample_paths or w["cpu_paths"])
     torch.set_num_threads(os.cpu_count() or 1)
-    if workload == "gbm":
+    if workload == "gbm_store":
+        spec = sm.Gbm(0.02, 0.3, torch.tensor([1.]), 1).kernel_spec()
+        run = lambda: (float(tp.diffusion_solve(spec, 3, 252, n)[0][:, -1].mean()), 0.0, 0.0)
+    elif workload == "merton_store":
+        spec = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1).kernel_spec()
+        run = lambda: (float(tp.jump_solve(spec, 3, 100, n, low_storage=False)[0][:, -1].mean()), 0.0, 0.0)
+    elif workload == "gbm":
         spec = sm.Gbm(0.02, 0.3, torch.tensor([1.]), 1).kernel_spec()
         run = lambda: tp.mc_simple_batched(spec, 3, 252, n, n, tp.payoff_call_on("euro_call", 1.0), 0.02, False, "terminal")
     elif workload == "levy2d":
@@ -197,8 +210,21 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident leg: inputs (a parameter struct + Philox key) are already on the device side ----
+    storing = args.workload.endswith("_store")
+    store_bytes = [0]
+
+    def store_step():
+        # the solve() contract: trajectories in the reference's layouts, resident in HBM (each rank its own paths)
+        out = solver.solve(bs=paths)
+        tensors = [out[0]] + [t for t in (out[1] if isinstance(out[1], tuple) else (out[1],)) if torch.is_tensor(t)]
+        store_bytes[0] = sum(t.numel() * t.element_size() for t in tensors) if not solver.has_jumps else \
+            sum(t.numel() * t.element_size() for t in tensors[1:]) + out[0].shape[0] * (solver.num_steps + solver.max_jumps + 1) * out[0].shape[2] * 4
+        return out
+
     def device_step():
         # every rank: `paths` paths of its own global path-id range (weak scaling), then the 64-byte all-reduce
+        if storing:
+            return store_step()
         if nets is not None:
             return sm.mc_cv_fused(nets, solver, paths * world, payoff, discounter)
         return E.run_moments(solver, payoff, discounter, paths * world, index_mode)
@@ -220,14 +246,25 @@ def main():
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    result = mom.read()
+    if storing:
+        last = mom
+        mom = None
+        final = last[0][:, -1, 0].double()
+        result = {"sum": float(final.sum()), "sumsq": float((final * final).sum()), "n": float(paths),
+                  "iters": float(paths) * w["num_steps"]}
+        del last, final
+    else:
+        result = mom.read()
 
     # ---- end-to-end leg: the public API call a user makes, host struct in -> python floats out ----
     barrier()
     t0 = time.perf_counter()
     stats = None
     for _ in range(args.steps):
-        if nets is not None:
+        if storing:
+            stats = store_step()
+            stats = None
+        elif nets is not None:
             stats = sm.mc_apply_cvs(nets, solver, paths * world, payoff, discounter, sim_bs=10 ** 5, bs=2000)
         else:
             stats = sm.mc_simple(paths * world, solver, payoff, discounter, bs=10 ** 6, payoff_time=payoff_time)
@@ -278,6 +315,21 @@ def main():
             "estimate": {"mean": mean, "stderr": se, "n": n_total,
                          "closed_form": {"gbm": 0.22943206, "levy2d": None}.get(args.workload, 0.26298121)},
         }
+        if storing:
+            gbs = store_bytes[0] * args.steps / (dev_ms * 1e-3) / 1e9
+            peaks = {}
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                    peaks = json.load(fh)
+            except OSError:
+                pass
+            hpeak = peaks.get("hbm_gbs", 6650.0)
+            out["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hpeak, "unit": "GB/s", "frac": gbs / hpeak,
+                               "traffic": None, "bytes_per_step": store_bytes[0],
+                               "peak_def": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6.65 TB/s"}
+            out["e2e"]["call"] = "solver.solve(bs=paths)  (trajectories stay on the device, as in the reference)"
+            out["e2e"]["d2h_bytes_per_step"] = 0
+            out["estimate"] = {"mean_terminal_state": result["sum"] / result["n"], "n": result["n"]}
         if nets is not None:
             iters_per_s = result["iters"] / (dev_ms * 1e-3) * args.steps / world
             tf = CV_TENSOR_FLOP_PER_ITER * iters_per_s / 1e12

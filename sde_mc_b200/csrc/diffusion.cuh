@@ -1,6 +1,7 @@
 // diffusion.cuh -- fused uniform-grid kernels: DiffusionSolver.solve (solvers.py:68-88) + payoff + moments.
 #pragma once
 #include "engine.cuh"
+#include "store_tile.cuh"
 
 namespace sdemc {
 
@@ -22,18 +23,30 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
   constexpr bool FAST1D = DIM == 1 && M == 1 && !HESTON && !INJECT && !STORE;
   const int S = s.num_steps;
 
+  extern __shared__ float diff_store_smem[];  // STORE: two staging tiles per warp (paths, increments)
+  using Writer = WarpTileWriter<32>;
+  Writer wpaths, wnorm;
+
   Accum acc;
   acc.zero();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
+  // warp-uniform trip count: in STORE mode all 32 lanes stage their outputs in lock-step, so lanes past the end of
+  // the range keep iterating (their rows are never written)
+  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < rg.n_paths; wbase += stride) {
+    const uint64_t i = wbase + (threadIdx.x & 31);
+    if (!STORE && i >= rg.n_paths) break;
+    const bool valid = i < rg.n_paths;
     const uint64_t gp = rg.path_lo + i;
     const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
     float x[kMaxDim];
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) x[d] = d < DIM ? s.x0[d] : 0.0f;
-    if (STORE && out.paths) {
+    if (STORE) {
+      float* tiles = diff_store_smem + (threadIdx.x >> 5) * (2 * Writer::kFloats);
+      wpaths.init(tiles, out.paths, (uint64_t)(S + 1) * DIM, wbase, rg.n_paths);
+      wnorm.init(tiles + Writer::kFloats, out.normals, (uint64_t)S * DIM * M, wbase, rg.n_paths);
 #pragma unroll
-      for (int d = 0; d < DIM; ++d) out.paths[(i * (uint64_t)(S + 1)) * DIM + d] = x[d];
+      for (int d = 0; d < DIM; ++d) wpaths.append(x[d]);
     }
 
     int b_first = 0;
@@ -77,7 +90,7 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
         for (int sp = 0; sp < SPB; ++sp) {
           const int step = b * SPB + sp;
           extra[sp] = 0.0f;
-          if (step < S) {
+          if (step < S && valid) {
             const float* zp = inj.z + (i * (uint64_t)S + step) * (DIM * M);
 #pragma unroll
             for (int q = 0; q < NZ; ++q) nrm[sp * NZ + q] = zp[q];
@@ -100,19 +113,14 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
           if (HESTON) heston_step_uniform(s, x, w1);
           else euler_step_uniform<C>(s, x, w1, w2);
           if (STORE) {
-            if (out.paths) {
 #pragma unroll
-              for (int d = 0; d < DIM; ++d) out.paths[(i * (uint64_t)(S + 1) + step + 1) * DIM + d] = x[d];
-            }
-            if (out.normals) {
-              float* np = out.normals + (i * (uint64_t)S + step) * (DIM * M);
+            for (int d = 0; d < DIM; ++d) wpaths.append(x[d]);
 #pragma unroll
-              for (int d = 0; d < BASE; ++d) {
-                np[d * M] = w1[d] * s.sqrt_h0;
-                if (M == 2) np[d * M + 1] = w2[d] * s.sqrt_h0;
-              }
-              if (C::ASIAN) np[BASE * M] = extra[sp] * s.sqrt_h0;
+            for (int d = 0; d < BASE; ++d) {
+              wnorm.append(w1[d] * s.sqrt_h0);
+              if (M == 2) wnorm.append(w2[d] * s.sqrt_h0);
             }
+            if (C::ASIAN) wnorm.append(extra[sp] * s.sqrt_h0);
           }
         }
       }
@@ -120,8 +128,10 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
 
     const float pay = eval_payoff<DIM>(po, x);
     if (STORE) {
-      if (out.payoffs) out.payoffs[i] = pay;
-      if (out.iters) out.iters[i] = S;
+      wpaths.flush();
+      wnorm.flush();
+      if (valid && out.payoffs) out.payoffs[i] = pay;
+      if (valid && out.iters) out.iters[i] = S;
     } else {
       acc.add(pay, po.df * x[0] - s.x0[0], S);  // terminal control  D(T) x_T[0] - x_0[0]  mc.py:337
     }

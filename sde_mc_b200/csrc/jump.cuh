@@ -10,6 +10,7 @@
 // Deviation: dt is clamped at 0 where the reference would trip `assert next_jump_time >= t` (:193).
 #pragma once
 #include "engine.cuh"
+#include "store_tile.cuh"
 
 namespace sdemc {
 
@@ -170,12 +171,21 @@ struct JumpState {
   bool need_pop;
 };
 
+// what one iteration produced, for the path-storing mode (solvers.py:205-222)
+struct StepRecord {
+  float left[kMaxDim];  // state after the diffusion step, before the jump
+  float dw1[kMaxDim];   // first-driver increments actually used
+  float dw2;            // common second-driver increment
+  float Jc;             // applied jump mark (0 if none)
+  float sq;             // sqrt(dt) of the iteration
+};
+
 // one iteration of the while-loop solvers.py:182-225.  zn: this iteration's unit normals
 // (BASE correlated-driver normals, then the common second-driver normal if M == 2).
 template <class C, class Src, bool STORE>
 __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys& keys, JumpState& st, Src& src,
-                                               const float* zn, const DevOut& out, uint64_t row, float extra_z) {
-  constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M;
+                                               const float* zn, StepRecord& rec) {
+  constexpr int BASE = C::BASE, M = C::M;
   src.begin_iter(s, keys, st.k);
   src.advance(s, keys, st.need_pop);
   const float tau = src.tau;
@@ -193,39 +203,24 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
   euler_step<C>(s, st.x, dt, sq, w1, w2);
   st.t += dt;
   const bool hit = fabsf(tau - st.t) <= fmaf(fabsf(st.t), 1e-5f, 1e-12f);
-  if (STORE && out.left) {
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) out.left[(row * (uint64_t)(out.S + 1) + st.k + 1) * DIM + d] = st.x[d];
-  }
   // branch-free: a zero mark leaves the state untouched (x + c x_base * 0)
   const float Jc = hit ? src.mark(s, st.k) : 0.0f;
+  if (STORE) {
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) {
+      rec.left[i] = st.x[i];
+      rec.dw1[i] = i < BASE ? w1[i] * sq : 0.0f;
+    }
+    rec.dw2 = M == 2 ? zn[BASE] * sq : 0.0f;
+    rec.Jc = Jc;
+    rec.sq = sq;
+  }
   if (s.exact_jumps) {
 #pragma unroll
     for (int i = 0; i < kMaxDim; ++i) xo[i] = st.x[i];
   }
   add_jump<C>(s, st.x, xo, Jc);
   st.need_pop = hit;
-  if (STORE) {
-    const uint64_t o1 = row * (uint64_t)(out.S + 1) + st.k + 1;
-    if (out.paths) {
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) out.paths[o1 * DIM + d] = st.x[d];
-    }
-    if (out.jumps) {
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) out.jumps[o1 * DIM + d] = Jc;
-    }
-    if (out.times) out.times[o1] = st.t;
-    if (out.normals) {
-      float* np = out.normals + (row * (uint64_t)out.S + st.k) * (DIM * M);
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        const float wd = d < BASE ? w1[d] * sq : extra_z * sq;
-        np[d * M] = wd;
-        if (M == 2) np[d * M + 1] = w2[d < BASE ? d : 0] * sq;
-      }
-    }
-  }
   ++st.k;
 }
 
@@ -257,12 +252,21 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
     __syncthreads();
   }
 
+  using Writer = WarpTileWriter<16>;
+  Writer w_paths, w_left, w_jumps, w_times, w_norm;  // STORE: five staging tiles per warp, after the jump queue
+  float* store_tiles = reinterpret_cast<float*>(jump_queue_smem + (JSRC == JSRC_QUEUE ? qdepth * blockDim.x : 0)) +
+                       (threadIdx.x >> 5) * (5 * Writer::kFloats);
+
   Accum acc;
   acc.zero();
   int local_max_iters = 0;
   const int n = s.num_steps;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
+  // warp-uniform trip count (see diffusion.cuh): STORE stages its outputs with all 32 lanes in lock-step
+  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < rg.n_paths; wbase += stride) {
+    const uint64_t i = wbase + (threadIdx.x & 31);
+    if (!STORE && i >= rg.n_paths) break;
+    const bool valid = i < rg.n_paths;
     const uint64_t gp = rg.path_lo + i;
     const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
     JumpState st;
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
     st.k = 0;
     st.need_pop = true;
     Src src;
-    if constexpr (JSRC == JSRC_INJECT) src.init(s, inj, i);
+    if constexpr (JSRC == JSRC_INJECT) src.init(s, inj, valid ? i : 0);
     else if constexpr (JSRC == JSRC_QUEUE) src.init(qdepth, plo, phi);
     else src.init(plo, phi);
 
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
           extra[sp] = 0.0f;
 #pragma unroll
           for (int q = 0; q < NZ; ++q) nrm[sp * NZ + q] = 0.0f;
-          if (k < inj.K) {
+          if (k < inj.K && valid) {
             const float* zp = inj.z + (i * (uint64_t)inj.K + k) * DIM;
 #pragma unroll
             for (int q = 0; q < BASE; ++q) nrm[sp * NZ + q] = zp[q];
@@ -311,19 +315,19 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
     if (STORE) {
       // lock-step over the whole allocation: finished paths idle with dt = 0 exactly as in the reference,
       // where the loop runs until the slowest path of the batch is done (:182).
-      if (out.paths) {
+      const uint64_t S1 = (uint64_t)out.S + 1;
+      w_paths.init(store_tiles + 0 * Writer::kFloats, out.paths, S1 * DIM, wbase, rg.n_paths);
+      w_left.init(store_tiles + 1 * Writer::kFloats, out.left, S1 * DIM, wbase, rg.n_paths);
+      w_jumps.init(store_tiles + 2 * Writer::kFloats, out.jumps, S1 * DIM, wbase, rg.n_paths);
+      w_times.init(store_tiles + 3 * Writer::kFloats, out.times, S1, wbase, rg.n_paths);
+      w_norm.init(store_tiles + 4 * Writer::kFloats, out.normals, (uint64_t)out.S * DIM * M, wbase, rg.n_paths);
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) out.paths[(i * (uint64_t)(out.S + 1)) * DIM + d] = st.x[d];
+      for (int d = 0; d < DIM; ++d) {
+        w_paths.append(st.x[d]);
+        w_left.append(st.x[d]);
+        w_jumps.append(0.0f);
       }
-      if (out.left) {
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) out.left[(i * (uint64_t)(out.S + 1)) * DIM + d] = st.x[d];
-      }
-      if (out.jumps) {
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) out.jumps[(i * (uint64_t)(out.S + 1)) * DIM + d] = 0.0f;
-      }
-      if (out.times) out.times[i * (uint64_t)(out.S + 1)] = 0.0f;
+      w_times.append(0.0f);
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
       for (int b = 0; b * SPB < out.S; ++b) {
@@ -333,7 +337,21 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
         for (int sp = 0; sp < SPB; ++sp) {
           if (st.k < out.S) {
             if (st.t < s.T) own_iters = st.k + 1;
-            jump_iteration<C, Src, true>(s, keys, st, src, nrm + sp * NZ, out, i, extra[sp]);
+            StepRecord rec;
+            jump_iteration<C, Src, true>(s, keys, st, src, nrm + sp * NZ, rec);
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+              w_left.append(rec.left[d]);
+              w_paths.append(st.x[d]);
+              w_jumps.append(rec.Jc);
+              if (d < BASE) {
+                w_norm.append(rec.dw1[d]);
+                if (M == 2) w_norm.append(rec.dw2);
+              } else {
+                w_norm.append(extra[sp] * rec.sq);  // injected normal of the asian integral component
+              }
+            }
+            w_times.append(st.t);
             if (st.k == n) {
 #pragma unroll
               for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
@@ -341,15 +359,21 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
           }
         }
       }
+      w_paths.flush();
+      w_left.flush();
+      w_jumps.flush();
+      w_times.flush();
+      w_norm.flush();
     } else {
       // phase 1: the first num_steps iterations can never reach T (each advances by at most T/num_steps),
       // so full Philox blocks run without the loop-exit test.
+      StepRecord rec_unused;
       const int nb_full = n / SPB;
       for (int b = 0; b < nb_full; ++b) {
         float nrm[NBUF], extra[SPB];
         load_normals(b, nrm, extra);
 #pragma unroll
-        for (int sp = 0; sp < SPB; ++sp) jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZ, out, i, 0.0f);
+        for (int sp = 0; sp < SPB; ++sp) jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZ, rec_unused);
       }
       if (st.k == n) {
 #pragma unroll
@@ -365,7 +389,7 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
 #pragma unroll
         for (int sp = 0; sp < SPB; ++sp) {
           if (!done) {
-            jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZ, out, i, 0.0f);
+            jump_iteration<C, Src, false>(s, keys, st, src, nrm + sp * NZ, rec_unused);
             if (st.k == n) {
 #pragma unroll
               for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
@@ -382,9 +406,9 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
     for (int d = 0; d < kMaxDim; ++d) xp[d] = po.index_mode == SDEMC_INDEX_TERMINAL ? xs[d] : st.x[d];
     const float pay = eval_payoff<DIM>(po, xp);
     if (STORE) {
-      if (out.payoffs) out.payoffs[i] = pay;
-      if (out.iters) out.iters[i] = own_iters;
-      local_max_iters = max(local_max_iters, own_iters);
+      if (valid && out.payoffs) out.payoffs[i] = pay;
+      if (valid && out.iters) out.iters[i] = own_iters;
+      if (valid) local_max_iters = max(local_max_iters, own_iters);
     } else {
       acc.add(pay, po.df * st.x[0] - s.x0[0], own_iters);
     }

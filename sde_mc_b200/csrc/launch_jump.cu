@@ -10,7 +10,8 @@ namespace {
 template <class C, int JSRC, bool STORE>
 int run(const LaunchArgs& a) {
   auto kernel = jump_kernel<C, JSRC, STORE>;
-  const size_t smem = JSRC == JSRC_QUEUE ? (size_t)a.qdepth * kBlock * sizeof(float2) : 0;
+  const size_t smem = (JSRC == JSRC_QUEUE ? (size_t)a.qdepth * kBlock * sizeof(float2) : 0) +
+                      (STORE ? (size_t)(kBlock / 32) * 5 * WarpTileWriter<16>::kFloats * sizeof(float) : 0);
   if (smem > 48 * 1024) SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = 0;
   int rc = pick_grid(kernel, smem, a.range.n_paths, &grid);
