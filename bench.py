@@ -236,6 +236,7 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    device_step()          # untimed: the GPU idled while the clock sampler started; bring it back under load
     stream = torch.cuda.current_stream(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SDEMC_ABI_VERSION 1
+#define SDEMC_ABI_VERSION 2
 #define SDEMC_MAX_DIM 4
 #define SDEMC_MAX_LEVELS 16
 
@@ -142,7 +142,10 @@ typedef struct {
 } sdemc_moments;
 
 /* Optional trajectory outputs, layouts exactly as the reference allocates them (solvers.py:64-66,150-162).
- * S = num_steps for the diffusion solver, num_steps + max_jumps for the jump solver.  NULL = skip. */
+ * S = num_steps for the diffusion solver, num_steps + max_jumps for the jump solver.  NULL = skip.
+ * Rows (one per path) may be padded: pitch_* = floats between consecutive rows, 0 = dense (the reference's
+ * contiguous layout).  With a pitch that is a multiple of 4 floats and 16-byte aligned bases the kernels write
+ * 16-byte vectors covering whole 128-byte lines; any other pitch takes the 4-byte store path. */
 typedef struct {
   float* d_paths;       /* (n, S+1, dim) */
   float* d_left;        /* (n, S+1, dim)  state before the jump            (jump solver) */
@@ -152,6 +155,9 @@ typedef struct {
   float* d_payoffs;     /* (n)            discounted payoff per path */
   int32_t* d_iters;     /* (n)            executed iterations per path */
   int32_t* d_total_steps; /* scalar: max over paths of executed iterations (atomicMax; caller zeroes it) */
+  int64_t pitch_state;    /* row pitch of d_paths / d_left / d_jumps, 0 = (S+1)*dim */
+  int64_t pitch_times;    /* row pitch of d_times, 0 = S+1 */
+  int64_t pitch_normals;  /* row pitch of d_normals, 0 = S*dim*m */
 } sdemc_paths_out;
 
 /* Control-variate networks for the fused CV kernel: the BN-free Mlp of nets.py:39-93,

@@ -51,7 +51,8 @@ class SdemcInject(C.Structure):
 class SdemcPathsOut(C.Structure):
     _fields_ = [("d_paths", C.c_void_p), ("d_left", C.c_void_p), ("d_times", C.c_void_p), ("d_jumps", C.c_void_p),
                 ("d_normals", C.c_void_p), ("d_payoffs", C.c_void_p), ("d_iters", C.c_void_p),
-                ("d_total_steps", C.c_void_p)]
+                ("d_total_steps", C.c_void_p), ("pitch_state", C.c_int64), ("pitch_times", C.c_int64),
+                ("pitch_normals", C.c_int64)]
 
 
 class SdemcMlp(C.Structure):

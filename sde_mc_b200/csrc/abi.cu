@@ -58,10 +58,12 @@ static int solve_common(const sdemc_sde* sde, const sdemc_payoff* payoff, const 
   a.qdepth = choose_qdepth(*sde);
   if (jumps) {
     const int S = inject ? inject->K : sde->num_steps + sde->max_jumps;
-    a.out = to_dev(out, S);
+    if (!valid_pitches(out, S, sde->dim, sde->dim * sde->m)) return SDEMC_ERR_BAD_ARG;
+    a.out = to_dev(out, S, sde->dim, sde->dim * sde->m);
     return launch_jump(*sde, a);
   }
-  a.out = to_dev(out, sde->num_steps);
+  if (!valid_pitches(out, sde->num_steps, sde->dim, sde->dim * sde->m)) return SDEMC_ERR_BAD_ARG;
+  a.out = to_dev(out, sde->num_steps, sde->dim, sde->dim * sde->m);
   return launch_diffusion(*sde, a);
 }
 

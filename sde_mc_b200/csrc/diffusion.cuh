@@ -11,8 +11,24 @@ namespace sdemc {
 #ifndef SDEMC_DIFF_MIN_BLOCKS
 #define SDEMC_DIFF_MIN_BLOCKS 1
 #endif
+// staging tile of the path-storing mode: 32 elements per path and flush; a step group stages up to
+// steps_per_group * max(dim, increments per step) elements
+#ifndef SDEMC_DIFF_STORE_TILE
+#define SDEMC_DIFF_STORE_TILE 32
+#endif
+#ifndef SDEMC_DIFF_STORE_MINB
+#define SDEMC_DIFF_STORE_MINB 1
+#endif
+template <class C>
+using DiffusionStoreWriter =
+    WarpTileWriter<SDEMC_DIFF_STORE_TILE, steps_per_group(C::BASE * C::M) * (C::DIM > C::BASE * C::M + (C::ASIAN ? 1 : 0)
+                                                              ? C::DIM
+                                                              : C::BASE * C::M + (C::ASIAN ? 1 : 0))>;
+
+constexpr int kDiffusionStoreBlock = 128;  // threads per CTA of the storing kernels (shared tiles limit residency)
+
 template <class C, bool HESTON, bool INJECT, bool STORE>
-__global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BLOCKS) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+__global__ void __launch_bounds__(256, STORE ? SDEMC_DIFF_STORE_MINB : (INJECT ? 1 : SDEMC_DIFF_MIN_BLOCKS)) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                         const PhiloxKeys keys, const DevInject inj, const DevOut out,
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
   constexpr int DIM = C::DIM, M = C::M, BASE = C::BASE;
@@ -24,7 +40,7 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
   const int S = s.num_steps;
 
   extern __shared__ float diff_store_smem[];  // STORE: two staging tiles per warp (paths, increments)
-  using Writer = WarpTileWriter<32>;
+  using Writer = DiffusionStoreWriter<C>;
   Writer wpaths, wnorm;
 
   Accum acc;
@@ -43,8 +59,8 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
     for (int d = 0; d < kMaxDim; ++d) x[d] = d < DIM ? s.x0[d] : 0.0f;
     if (STORE) {
       float* tiles = diff_store_smem + (threadIdx.x >> 5) * (2 * Writer::kFloats);
-      wpaths.init(tiles, out.paths, (uint64_t)(S + 1) * DIM, wbase, rg.n_paths);
-      wnorm.init(tiles + Writer::kFloats, out.normals, (uint64_t)S * DIM * M, wbase, rg.n_paths);
+      wpaths.init(tiles, out.paths, out.pitch_state, wbase, rg.n_paths);
+      wnorm.init(tiles + Writer::kFloats, out.normals, out.pitch_normals, wbase, rg.n_paths);
 #pragma unroll
       for (int d = 0; d < DIM; ++d) wpaths.append(x[d]);
     }
@@ -98,6 +114,9 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
           }
         }
       }
+      // STORE: the group's outputs are staged at compile-time slots and committed once (store_tile.cuh); steps past
+      // the end of the grid stage nothing that is committed.
+      constexpr int NPS = BASE * M + (C::ASIAN ? 1 : 0);  // increments recorded per step
 #pragma unroll
       for (int sp = 0; sp < SPB; ++sp) {
         const int step = b * SPB + sp;
@@ -114,15 +133,20 @@ __global__ void __launch_bounds__(256, (STORE || INJECT) ? 1 : SDEMC_DIFF_MIN_BL
           else euler_step_uniform<C>(s, x, w1, w2);
           if (STORE) {
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) wpaths.append(x[d]);
+            for (int d = 0; d < DIM; ++d) wpaths.stage(sp * DIM + d, x[d]);
 #pragma unroll
             for (int d = 0; d < BASE; ++d) {
-              wnorm.append(w1[d] * s.sqrt_h0);
-              if (M == 2) wnorm.append(w2[d] * s.sqrt_h0);
+              wnorm.stage(sp * NPS + d * M, w1[d] * s.sqrt_h0);
+              if (M == 2) wnorm.stage(sp * NPS + d * M + 1, w2[d] * s.sqrt_h0);
             }
-            if (C::ASIAN) wnorm.append(extra[sp] * s.sqrt_h0);
+            if (C::ASIAN) wnorm.stage(sp * NPS + BASE * M, extra[sp] * s.sqrt_h0);
           }
         }
+      }
+      if (STORE) {
+        const int done = min(SPB, S - b * SPB);
+        wpaths.commit(done * DIM);
+        wnorm.commit(done * NPS);
       }
     }
 

@@ -63,6 +63,7 @@ struct DevOut {
   int* iters;
   int* total_steps;
   int S;  // allocated iterations per path (rows are S+1 / S long)
+  uint64_t pitch_state, pitch_times, pitch_normals;  // floats between consecutive path rows
 };
 
 // compile-time configuration of a kernel instance

@@ -109,27 +109,41 @@ inline DevInject to_dev(const sdemc_inject* j) {
   return d;
 }
 
-inline DevOut to_dev(const sdemc_paths_out* o, int S) {
+// normals_per_step: floats of the increments array per iteration (dim * m; dim for the 'diag' jump solver)
+inline DevOut to_dev(const sdemc_paths_out* o, int S, int dim = 1, int normals_per_step = 1) {
   DevOut d;
   std::memset(&d, 0, sizeof d);
+  d.S = S;
+  d.pitch_state = (uint64_t)(S + 1) * dim;
+  d.pitch_times = (uint64_t)(S + 1);
+  d.pitch_normals = (uint64_t)S * normals_per_step;
   if (o) {
     d.paths = o->d_paths; d.left = o->d_left; d.times = o->d_times; d.jumps = o->d_jumps;
     d.normals = o->d_normals; d.payoffs = o->d_payoffs; d.iters = o->d_iters; d.total_steps = o->d_total_steps;
+    if (o->pitch_state > 0) d.pitch_state = (uint64_t)o->pitch_state;
+    if (o->pitch_times > 0) d.pitch_times = (uint64_t)o->pitch_times;
+    if (o->pitch_normals > 0) d.pitch_normals = (uint64_t)o->pitch_normals;
   }
-  d.S = S;
   return d;
+}
+inline bool valid_pitches(const sdemc_paths_out* o, int S, int dim, int normals_per_step) {
+  if (!o) return true;
+  if (o->pitch_state != 0 && o->pitch_state < (int64_t)(S + 1) * dim) return false;
+  if (o->pitch_times != 0 && o->pitch_times < (int64_t)(S + 1)) return false;
+  if (o->pitch_normals != 0 && o->pitch_normals < (int64_t)S * normals_per_step) return false;
+  return true;
 }
 
 // persistent-style grid: a whole number of waves of resident CTAs, never more threads than paths
 template <class Kernel>
-inline int pick_grid(Kernel kernel, size_t dyn_smem, uint64_t n_paths, int* out_grid) {
+inline int pick_grid(Kernel kernel, size_t dyn_smem, uint64_t n_paths, int* out_grid, int block = kBlock) {
   int dev = 0, sms = 0, per_sm = 0;
   SDEMC_CUDA_CHECK(cudaGetDevice(&dev));
   SDEMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  SDEMC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, dyn_smem));
+  SDEMC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, dyn_smem));
   if (per_sm < 1) per_sm = 1;
   uint64_t grid = (uint64_t)sms * (uint64_t)per_sm;
-  const uint64_t need = (n_paths + kBlock - 1) / kBlock;
+  const uint64_t need = (n_paths + block - 1) / block;
   if (need < grid) grid = need;
   if (grid < 1) grid = 1;
   const uint64_t cap = (kWorkspaceBytes - 64) / (kNumMoments * sizeof(double));

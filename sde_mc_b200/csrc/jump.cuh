@@ -227,11 +227,23 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
 // ------------------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------------------
+// staging tiles of the path-storing mode: 16 elements per path and flush, five arrays; a group of iterations
+// stages up to steps_per_group * dim * m elements per array
+#ifndef SDEMC_JUMP_STORE_TILE
+#define SDEMC_JUMP_STORE_TILE 16
+#endif
+#ifndef SDEMC_JUMP_STORE_MINB
+#define SDEMC_JUMP_STORE_MINB 1
+#endif
+template <class C>
+using JumpStoreWriter = WarpTileWriter<SDEMC_JUMP_STORE_TILE, steps_per_group(C::BASE + (C::M == 2 ? 1 : 0)) * C::DIM * C::M>;
+constexpr int kJumpStoreBlock = 128;  // threads per CTA of the storing kernels (their shared tiles limit residency)
+
 #ifndef SDEMC_JUMP_MIN_BLOCKS
 #define SDEMC_JUMP_MIN_BLOCKS 4  // <= 64 registers per thread: 32 resident warps per SM
 #endif
 template <class C, int JSRC, bool STORE>
-__global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+__global__ void __launch_bounds__(256, STORE ? SDEMC_JUMP_STORE_MINB : SDEMC_JUMP_MIN_BLOCKS) jump_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                    const PhiloxKeys keys, const DevInject inj, const DevOut out,
                                                    const int qdepth, double* __restrict__ d_moments,
                                                    void* __restrict__ d_ws) {
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
     __syncthreads();
   }
 
-  using Writer = WarpTileWriter<16>;
+  using Writer = JumpStoreWriter<C>;
   Writer w_paths, w_left, w_jumps, w_times, w_norm;  // STORE: five staging tiles per warp, after the jump queue
   float* store_tiles = reinterpret_cast<float*>(jump_queue_smem + (JSRC == JSRC_QUEUE ? qdepth * blockDim.x : 0)) +
                        (threadIdx.x >> 5) * (5 * Writer::kFloats);
@@ -315,12 +327,11 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
     if (STORE) {
       // lock-step over the whole allocation: finished paths idle with dt = 0 exactly as in the reference,
       // where the loop runs until the slowest path of the batch is done (:182).
-      const uint64_t S1 = (uint64_t)out.S + 1;
-      w_paths.init(store_tiles + 0 * Writer::kFloats, out.paths, S1 * DIM, wbase, rg.n_paths);
-      w_left.init(store_tiles + 1 * Writer::kFloats, out.left, S1 * DIM, wbase, rg.n_paths);
-      w_jumps.init(store_tiles + 2 * Writer::kFloats, out.jumps, S1 * DIM, wbase, rg.n_paths);
-      w_times.init(store_tiles + 3 * Writer::kFloats, out.times, S1, wbase, rg.n_paths);
-      w_norm.init(store_tiles + 4 * Writer::kFloats, out.normals, (uint64_t)out.S * DIM * M, wbase, rg.n_paths);
+      w_paths.init(store_tiles + 0 * Writer::kFloats, out.paths, out.pitch_state, wbase, rg.n_paths);
+      w_left.init(store_tiles + 1 * Writer::kFloats, out.left, out.pitch_state, wbase, rg.n_paths);
+      w_jumps.init(store_tiles + 2 * Writer::kFloats, out.jumps, out.pitch_state, wbase, rg.n_paths);
+      w_times.init(store_tiles + 3 * Writer::kFloats, out.times, out.pitch_times, wbase, rg.n_paths);
+      w_norm.init(store_tiles + 4 * Writer::kFloats, out.normals, out.pitch_normals, wbase, rg.n_paths);
 #pragma unroll
       for (int d = 0; d < DIM; ++d) {
         w_paths.append(st.x[d]);
@@ -331,33 +342,54 @@ __global__ void __launch_bounds__(256, STORE ? 1 : SDEMC_JUMP_MIN_BLOCKS) jump_k
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
       for (int b = 0; b * SPB < out.S; ++b) {
+        // Once every path of the warp has reached T and none has a jump pending at T, the remaining iterations are
+        // idle (dt = 0: state, time and the zero increments repeat); write them without running the loop body.
+        const bool idle = !(st.t < s.T) && !st.need_pop && !(fabsf(src.tau - st.t) <= fmaf(fabsf(st.t), 1e-5f, 1e-12f));
+        if (__all_sync(0xffffffffu, idle)) break;
         float nrm[NBUF], extra[SPB];
         load_normals(b, nrm, extra);
+        const int done = min(SPB, out.S - st.k);  // iterations of this group inside the allocation (warp-uniform)
 #pragma unroll
         for (int sp = 0; sp < SPB; ++sp) {
-          if (st.k < out.S) {
+          if (sp < done) {
             if (st.t < s.T) own_iters = st.k + 1;
             StepRecord rec;
             jump_iteration<C, Src, true>(s, keys, st, src, nrm + sp * NZ, rec);
 #pragma unroll
             for (int d = 0; d < DIM; ++d) {
-              w_left.append(rec.left[d]);
-              w_paths.append(st.x[d]);
-              w_jumps.append(rec.Jc);
+              w_left.stage(sp * DIM + d, rec.left[d]);
+              w_paths.stage(sp * DIM + d, st.x[d]);
+              w_jumps.stage(sp * DIM + d, rec.Jc);
               if (d < BASE) {
-                w_norm.append(rec.dw1[d]);
-                if (M == 2) w_norm.append(rec.dw2);
+                w_norm.stage((sp * DIM + d) * M, rec.dw1[d]);
+                if (M == 2) w_norm.stage((sp * DIM + d) * M + 1, rec.dw2);
               } else {
-                w_norm.append(extra[sp] * rec.sq);  // injected normal of the asian integral component
+                w_norm.stage((sp * DIM + d) * M, extra[sp] * rec.sq);  // injected normal of the asian integral component
               }
             }
-            w_times.append(st.t);
+            w_times.stage(sp, st.t);
             if (st.k == n) {
 #pragma unroll
               for (int d = 0; d < kMaxDim; ++d) xs[d] = st.x[d];
             }
           }
         }
+        w_left.commit(done * DIM);
+        w_paths.commit(done * DIM);
+        w_jumps.commit(done * DIM);
+        w_norm.commit(done * DIM * M);
+        w_times.commit(done);
+      }
+      for (; st.k < out.S; ++st.k) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          w_left.append(st.x[d]);
+          w_paths.append(st.x[d]);
+          w_jumps.append(0.0f);
+#pragma unroll
+          for (int q = 0; q < M; ++q) w_norm.append(0.0f);
+        }
+        w_times.append(st.t);
       }
       w_paths.flush();
       w_left.flush();

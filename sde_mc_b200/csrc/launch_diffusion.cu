@@ -8,13 +8,14 @@ namespace {
 template <class C, bool HESTON, bool INJECT, bool STORE>
 int run(const LaunchArgs& a) {
   auto kernel = diffusion_kernel<C, HESTON, INJECT, STORE>;
-  const size_t smem = STORE ? (size_t)(kBlock / 32) * 2 * WarpTileWriter<32>::kFloats * sizeof(float) : 0;
+  const int block = STORE ? kDiffusionStoreBlock : kBlock;
+  const size_t smem = STORE ? (size_t)(block / 32) * 2 * DiffusionStoreWriter<C>::kFloats * sizeof(float) : 0;
   if (smem > 48 * 1024)
     SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = 0;
-  int rc = pick_grid(kernel, smem, a.range.n_paths, &grid);
+  int rc = pick_grid(kernel, smem, a.range.n_paths, &grid, block);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, a.d_moments, a.d_ws);
+  kernel<<<grid, block, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, a.d_moments, a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
 }

@@ -10,13 +10,14 @@ namespace {
 template <class C, int JSRC, bool STORE>
 int run(const LaunchArgs& a) {
   auto kernel = jump_kernel<C, JSRC, STORE>;
-  const size_t smem = (JSRC == JSRC_QUEUE ? (size_t)a.qdepth * kBlock * sizeof(float2) : 0) +
-                      (STORE ? (size_t)(kBlock / 32) * 5 * WarpTileWriter<16>::kFloats * sizeof(float) : 0);
+  const int block = STORE ? kJumpStoreBlock : kBlock;
+  const size_t smem = (JSRC == JSRC_QUEUE ? (size_t)a.qdepth * block * sizeof(float2) : 0) +
+                      (STORE ? (size_t)(block / 32) * 5 * JumpStoreWriter<C>::kFloats * sizeof(float) : 0);
   if (smem > 48 * 1024) SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = 0;
-  int rc = pick_grid(kernel, smem, a.range.n_paths, &grid);
+  int rc = pick_grid(kernel, smem, a.range.n_paths, &grid, block);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, a.qdepth, a.d_moments,
+  kernel<<<grid, block, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, a.qdepth, a.d_moments,
                                            a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;

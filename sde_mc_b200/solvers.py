@@ -18,6 +18,18 @@ from . import _spec
 from .schemes import EulerScheme, HestonScheme
 
 
+def _alloc_rows(bs, inner_shape, dev, align):
+    """(bs, *inner_shape) fp32 output whose rows (one per path) start `align` floats apart-aligned: the storing
+    kernels write 16-byte vectors / whole 128-byte lines when the row pitch allows it.  Returns (tensor, pitch);
+    with padding the tensor is a strided view (same shape and values as the reference's dense allocation)."""
+    length = int(np.prod(inner_shape))
+    pitch = -(-length // align) * align if align and align > 1 else length
+    buf = torch.empty((bs, pitch), device=dev, dtype=torch.float32)
+    if pitch == length:
+        return buf.view((bs,) + tuple(inner_shape)), pitch
+    return buf[:, :length].unflatten(1, tuple(inner_shape)), pitch
+
+
 def _as_dev_f32(a, dev):
     if a is None:
         return None
@@ -47,6 +59,10 @@ class SdeSolver(ABC):
         torch.manual_seed(seed)       # the reference reseeds torch's global RNG here (solvers.py:37)
         self._next_path = 0           # global Philox path id of the next path to simulate
         self.jump_strategy = L.JUMPS_AUTO
+        # Row pitch of stored trajectories in floats: rows are padded to a multiple of this (32 floats = one
+        # 128-byte line) so the path-storing kernels can use 16-byte vector stores.  Set to 1 for the reference's
+        # dense (contiguous) allocations -- same values, 4-byte store path.
+        self.row_align = 32
 
     # ---- engine plumbing -----------------------------------------------------------------------------------
     def _compute_device(self):
@@ -117,11 +133,11 @@ class DiffusionSolver(SdeSolver):
         m = self.sde.brown_dim // self.sde.dim
         sde = self._sde_struct()
         with torch.cuda.device(dev):
-            paths = torch.empty((bs, S + 1, d), device=dev, dtype=torch.float32)
-            nshape = (bs, S, d) if m == 1 else (bs, S, d, m)
-            normals = torch.empty(nshape, device=dev, dtype=torch.float32)
+            paths, p_state = _alloc_rows(bs, (S + 1, d), dev, self.row_align)
+            normals, p_norm = _alloc_rows(bs, (S, d) if m == 1 else (S, d, m), dev, self.row_align)
             payoffs = torch.empty((bs,), device=dev, dtype=torch.float32) if want_payoff is not None else None
-            out = L.SdemcPathsOut(L.ptr(paths), None, None, None, L.ptr(normals), L.ptr(payoffs), None, None)
+            out = L.SdemcPathsOut(L.ptr(paths), None, None, None, L.ptr(normals), L.ptr(payoffs), None, None,
+                                  p_state, 0, p_norm)
             inj = None
             keep = []
             if inject is not None:
@@ -210,18 +226,19 @@ class JumpDiffusionSolver(SdeSolver):
                 assert z.shape == (bs, S, d) and jt.shape == (bs, self.max_jumps) and mk.shape == (bs, S)
                 keep += [z, zc, jt, mk]
                 inj = L.SdemcInject(L.ptr(z), L.ptr(zc), L.ptr(jt), L.ptr(mk), S)
-            paths = torch.empty((bs, S + 1, d), device=dev, dtype=torch.float32)
+            paths, p_state = _alloc_rows(bs, (S + 1, d), dev, self.row_align)
+            p_times = p_norm = 0
             total = torch.zeros((1,), device=dev, dtype=torch.int32)
             iters = torch.empty((bs,), device=dev, dtype=torch.int32)
             payoffs = torch.empty((bs,), device=dev, dtype=torch.float32) if want_payoff is not None else None
             left = times = jumps = normals = None
             if not low_storage:
-                left = torch.empty_like(paths)
-                jumps = torch.empty_like(paths)
-                times = torch.empty((bs, S + 1), device=dev, dtype=torch.float32)
-                normals = torch.empty((bs, S, d) if m == 1 else (bs, S, d, m), device=dev, dtype=torch.float32)
+                left, _ = _alloc_rows(bs, (S + 1, d), dev, self.row_align)
+                jumps, _ = _alloc_rows(bs, (S + 1, d), dev, self.row_align)
+                times, p_times = _alloc_rows(bs, (S + 1,), dev, self.row_align)
+                normals, p_norm = _alloc_rows(bs, (S, d) if m == 1 else (S, d, m), dev, self.row_align)
             out = L.SdemcPathsOut(L.ptr(paths), L.ptr(left), L.ptr(times), L.ptr(jumps), L.ptr(normals),
-                                  L.ptr(payoffs), L.ptr(iters), L.ptr(total))
+                                  L.ptr(payoffs), L.ptr(iters), L.ptr(total), p_state, p_times, p_norm)
             rng = L.SdemcRange(int(self.seed), self._take_paths(bs), bs)
             L.check(lib.sdemc_solve_paths(sde, want_payoff, rng, inj, out, L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
             total_steps = int(total.item())
