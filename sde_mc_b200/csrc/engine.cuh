@@ -13,6 +13,7 @@
 namespace sdemc {
 
 constexpr int kMaxDim = SDEMC_MAX_DIM;
+constexpr int kBlock = 256;  // threads per CTA of the moments kernels
 
 // ------------------------------------------------------------------------------------------------------------
 // Device copies of the problem (passed by value as kernel parameters -> constant bank / uniform registers)

@@ -10,7 +10,6 @@
 
 namespace sdemc {
 
-constexpr int kBlock = 256;
 constexpr uint64_t kWorkspaceBytes = 1u << 20;  // ticket (64 B) + up to 16383 per-CTA partials
 
 void set_cuda_error(cudaError_t e, const char* where);

@@ -66,7 +66,8 @@ struct InjectJumps {
 // Cold path of the sparse-jump queue, deliberately out of line (one copy per kernel instead of one per unrolled
 // iteration): draws `qd` more (tau, J) pairs into this thread's queue column and returns the new running jump time.
 // Two Philox blocks give 4 jumps: 4 gap uniforms + 4 mark draws (2 Box-Muller pairs or 4 uniforms).
-template <int MARKS>
+// PREMUL: queue c[0] * J instead of J (1-D moments kernel, jump1d.cuh).
+template <int MARKS, bool PREMUL = false>
 __device__ __noinline__ float queue_refill(int qd, uint32_t chunk, uint32_t plo, uint32_t phi, float tau_acc) {
   const DevSde& s = g_sh_sde;
   const PhiloxKeys& keys = g_sh_keys;
@@ -87,7 +88,8 @@ __device__ __noinline__ float queue_refill(int qd, uint32_t chunk, uint32_t plo,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       tau_acc = fmaf(exp1_from_bits(g[j]), s.inv_rate, tau_acc);
-      jump_queue_smem[(r * 4 + j) * blockDim.x + threadIdx.x] = make_float2(tau_acc, mark_from_raw<MARKS>(s, raw[j]));
+      const float mark = mark_from_raw<MARKS>(s, raw[j]);
+      jump_queue_smem[(r * 4 + j) * blockDim.x + threadIdx.x] = make_float2(tau_acc, PREMUL ? s.c[0] * mark : mark);
     }
   }
   return tau_acc;

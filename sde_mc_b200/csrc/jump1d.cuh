@@ -1,0 +1,156 @@
+// jump1d.cuh -- moments-only fast path of the jump-adapted Euler loop for ONE-dimensional geometric jump diffusions
+// with sparse lognormal jumps (Merton, the north-star workload): JumpDiffusionSolver.solve solvers.py:164-226 with
+// low_storage semantics + payoff + (sum, sum^2).  Same arithmetic rules as jump.cuh (Q1-Q4 of SURVEY.md), restated
+// so that one loop iteration is ~14 instructions on top of its normal:
+//
+//   * the mesh is stateless.  The reference keeps h = min(h, max(T - t, 0)) (:190); t never decreases, so
+//     h_k = min(h0, max(T - t_k, 0)) and  dt = min(h, tau - t) = max(min(h0, min(tau, T) - t), 0)  (fp32 subtraction
+//     of the same t is monotone, so min(T - t, tau - t) == min(T, tau) - t bit for bit; the outer max is the dt >= 0
+//     clamp that replaces the reference's assert :193).
+//   * sigma is folded into the Box-Muller radius (z' = sigma z), the jump coefficient into the queued mark (c J).
+//   * the queue of pre-drawn (tau, c J) pairs is popped branch-free by bumping a shared-memory address on a hit.
+//     Whether a path ran out of queued jumps is checked once per group of 6 iterations (one Philox block of
+//     normals): the group runs speculatively from a saved (x, t, queue head); if the head left the filled part of
+//     the queue the group is replayed from the saved state with the per-iteration refill test (rare: a path needs
+//     more than `qdepth` jumps).  The Philox counters of normals and jumps are those of jump.cuh, so this kernel
+//     and the path-storing kernel simulate identical paths for the same seed.
+#pragma once
+#include "jump.cuh"
+
+namespace sdemc {
+
+constexpr int kQueueSlack = kNormalsPerBlock;  // slots a speculative group may read past the filled queue
+
+template <class C, bool EXACT>
+__global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
+    jump1d_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys, const int qdepth,
+                  double* __restrict__ d_moments, void* __restrict__ d_ws) {
+  static_assert(C::DIM == 1 && C::M == 1 && !C::ASIAN, "1-D single-driver models only");
+  constexpr int MARKS = C::MARKS;
+  constexpr int G = kNormalsPerBlock;  // iterations per group
+  constexpr bool GEO = C::FAMILY == SDEMC_FAMILY_GEOMETRIC;
+  if (threadIdx.x == 0) {
+    g_sh_sde = s;
+    g_sh_keys = keys;
+  }
+  __syncthreads();
+
+  const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(&jump_queue_smem[threadIdx.x]);
+  constexpr uint32_t q_stride = kBlock * (uint32_t)sizeof(float2);  // launched with kBlock threads (launch_jump.cu)
+  const uint32_t q_end = q_base + (uint32_t)qdepth * q_stride;
+  const float T = s.T, h0 = s.h0, a = s.a[0];
+  const float neg2ln2_b2 = -1.3862943611198906f * s.b1[0] * s.b1[0];
+  const int n = s.num_steps;
+  const int kcap = 4 * (n + s.max_jumps) + 64;
+
+  // fp64 running sums live in shared memory (one column per thread, touched once per path): 14 registers less in
+  // the step loop than a register-resident Accum
+  __shared__ double acc_sh[kNumMoments - 1][kBlock];
+#pragma unroll
+  for (int m = 0; m < kNumMoments - 1; ++m) acc_sh[m][threadIdx.x] = 0.0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
+    const uint64_t gp = rg.path_lo + i;
+    const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
+    float x = s.x0[0], t = 0.0f;
+    uint32_t chunk = 1;
+    float tau_acc = queue_refill<MARKS, true>(qdepth, 0u, plo, phi, 0.0f);  // initial fill
+    uint32_t q = q_base;
+
+    // one loop iteration.  CHECKED: refill test before the read (replay path); MASKED: the iteration only acts
+    // while t < T (phase 2), mirroring `while t < T` of the reference per path.
+    auto iteration = [&](float zs, auto checked, auto masked, int& k, float& x_at_n) {
+      if (decltype(checked)::value) {
+        if (q >= q_end) {
+          tau_acc = queue_refill<MARKS, true>(qdepth, chunk, plo, phi, tau_acc);
+          ++chunk;
+          q = q_base;
+        }
+      }
+      const bool active = decltype(masked)::value ? (t < T && k < kcap) : true;
+      const float2 e = lds_float2(q);  // (tau, c J)
+      const float dt = fmaxf(fminf(h0, fminf(e.x, T) - t), 0.0f);
+      const float sq = fast_sqrt(dt);
+      const float g = fmaf(sq, zs, a * dt);
+      const float xn = GEO ? fmaf(x, g, x) : x + g;
+      t += dt;
+      bool hit = fabsf(e.x - t) <= fmaf(fabsf(t), 1e-5f, 1e-12f);
+      if (decltype(masked)::value) hit = hit && active;
+      const float Jc = hit ? e.y : 0.0f;
+      if (GEO) x = fmaf(EXACT ? xn : x, Jc, xn);
+      else x = xn + Jc;
+      if (hit) q += q_stride;
+      if (decltype(masked)::value) {
+        k += active ? 1 : 0;
+        if (active && k == n) x_at_n = x;
+      }
+    };
+    auto group_normals = [&](int b, float(&zs)[G]) {
+      uint32_t o[4];
+      philox4x32_10((uint32_t)b, STREAM_DIFFUSION, plo, phi, keys, o);
+      float r[3], c[3], sn[3];
+      philox_polar3(o, neg2ln2_b2, r, c, sn);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        zs[2 * j] = r[j] * c[j];
+        zs[2 * j + 1] = r[j] * sn[j];
+      }
+    };
+
+    // phase 1: the first num_steps iterations can never reach T (each advances by at most T / num_steps): whole
+    // groups without the exit test, speculative on the queue.
+    int k = 0;
+    float x_at_n = x;
+    const int nb_full = n / G;
+    for (int b = 0; b < nb_full; ++b) {
+      float zs[G];
+      group_normals(b, zs);
+      const float xs = x, ts = t;
+      const uint32_t qs = q;
+#pragma unroll
+      for (int sp = 0; sp < G; ++sp) iteration(zs[sp], std::false_type(), std::false_type(), k, x_at_n);
+      if (q >= q_end) {  // ran out of queued jumps inside the group: replay it with the refill test
+        x = xs;
+        t = ts;
+        q = qs;
+        group_normals(b, zs);  // recomputed rather than kept live across the speculative group
+#pragma unroll
+        for (int sp = 0; sp < G; ++sp) iteration(zs[sp], std::true_type(), std::false_type(), k, x_at_n);
+        if (q >= q_end) {  // the next group must start on a valid head
+          tau_acc = queue_refill<MARKS, true>(qdepth, chunk, plo, phi, tau_acc);
+          ++chunk;
+          q = q_base;
+        }
+      }
+    }
+    k = nb_full * G;
+    if (k == n) x_at_n = x;
+    // phase 2: the remaining num_steps % 6 iterations and those forced by jumps, until t reaches T
+    for (int b = nb_full; t < T && k < kcap; ++b) {
+      float zs[G];
+      group_normals(b, zs);
+#pragma unroll
+      for (int sp = 0; sp < G; ++sp) iteration(zs[sp], std::true_type(), std::true_type(), k, x_at_n);
+    }
+
+    float xp[kMaxDim];
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) xp[d] = 0.0f;
+    xp[0] = po.index_mode == SDEMC_INDEX_TERMINAL ? x_at_n : x;
+    const float pay = eval_payoff<1>(po, xp);
+    {
+      Accum one;  // this path's contribution, folded into the thread's shared column
+      one.zero();
+      one.add(pay, po.df * x - s.x0[0], k);
+#pragma unroll
+      for (int m = 0; m < kNumMoments - 1; ++m) acc_sh[m][threadIdx.x] += one.v[m];
+    }
+  }
+  Accum acc;
+  acc.zero();
+#pragma unroll
+  for (int m = 0; m < kNumMoments - 1; ++m) acc.v[m] = acc_sh[m][threadIdx.x];
+  block_reduce_and_publish(acc, d_moments, d_ws);
+}
+
+}  // namespace sdemc

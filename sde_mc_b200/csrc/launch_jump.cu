@@ -1,7 +1,7 @@
 // launch_jump.cu -- instantiation + dispatch of the jump-adapted kernels (jump.cuh)
 #include <type_traits>
 
-#include "jump.cuh"
+#include "jump1d.cuh"
 #include "launch.cuh"
 
 namespace sdemc {
@@ -23,8 +23,28 @@ int run(const LaunchArgs& a) {
   return SDEMC_OK;
 }
 
+// moments-only fast path for 1-D single-driver models with queued (sparse) jumps: jump1d.cuh
+template <class C, bool EXACT>
+int run_1d(const LaunchArgs& a) {
+  auto kernel = jump1d_kernel<C, EXACT>;
+  const size_t smem = (size_t)(a.qdepth + kQueueSlack) * kBlock * sizeof(float2);
+  // always opt in: the kernel also has ~17 KB of static shared memory, so the 48 KB default can be exceeded by
+  // dynamic sizes below 48 KB
+  SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = 0;
+  int rc = pick_grid(kernel, smem, a.range.n_paths, &grid);
+  if (rc != SDEMC_OK) return rc;
+  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.qdepth, a.d_moments, a.d_ws);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+
 template <class C>
 int by_mode(const LaunchArgs& a) {
+  if constexpr (C::DIM == 1 && C::M == 1 && !C::ASIAN) {
+    if (!a.use_inject && !a.store && a.qdepth > 0)
+      return a.sde.exact_jumps ? run_1d<C, true>(a) : run_1d<C, false>(a);
+  }
   if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;
   if (a.qdepth > 0) return a.store ? run<C, JSRC_QUEUE, true>(a) : run<C, JSRC_QUEUE, false>(a);
   return a.store ? run<C, JSRC_INLINE, true>(a) : run<C, JSRC_INLINE, false>(a);
