@@ -1,13 +1,14 @@
 // jump1d.cuh -- moments-only fast path of the jump-adapted Euler loop for ONE-dimensional geometric jump diffusions
 // with sparse lognormal jumps (Merton, the north-star workload): JumpDiffusionSolver.solve solvers.py:164-226 with
 // low_storage semantics + payoff + (sum, sum^2).  Same arithmetic rules as jump.cuh (Q1-Q4 of SURVEY.md), restated
-// so that one loop iteration is ~14 instructions on top of its normal:
+// so that one loop iteration is ~15 instructions on top of its normal:
 //
 //   * the mesh is stateless.  The reference keeps h = min(h, max(T - t, 0)) (:190); t never decreases, so
 //     h_k = min(h0, max(T - t_k, 0)) and  dt = min(h, tau - t) = max(min(h0, min(tau, T) - t), 0)  (fp32 subtraction
 //     of the same t is monotone, so min(T - t, tau - t) == min(T, tau) - t bit for bit; the outer max is the dt >= 0
 //     clamp that replaces the reference's assert :193).
-//   * sigma is folded into the Box-Muller radius (z' = sigma z), the jump coefficient into the queued mark (c J).
+//   * sigma^2 and dt are folded into the Box-Muller radius (one square root per iteration instead of sqrt(dt) plus
+//     the radius root), the jump coefficient into the queued mark (c J).
 //   * the queue of pre-drawn (tau, c J) pairs is popped branch-free by bumping a shared-memory address on a hit.
 //     Whether a path ran out of queued jumps is checked once per group of 6 iterations (one Philox block of
 //     normals): the group runs speculatively from a saved (x, t, queue head); if the head left the filled part of
@@ -21,8 +22,11 @@ namespace sdemc {
 
 constexpr int kQueueSlack = kNormalsPerBlock;  // slots a speculative group may read past the filled queue
 
+#ifndef SDEMC_JUMP1D_MIN_BLOCKS
+#define SDEMC_JUMP1D_MIN_BLOCKS 3  // 80 registers, no spills in the step loop: measured 5% faster than 4 CTAs with spills
+#endif
 template <class C, bool EXACT>
-__global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
     jump1d_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys, const int qdepth,
                   double* __restrict__ d_moments, void* __restrict__ d_ws) {
   static_assert(C::DIM == 1 && C::M == 1 && !C::ASIAN, "1-D single-driver models only");
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
 
     // one loop iteration.  CHECKED: refill test before the read (replay path); MASKED: the iteration only acts
     // while t < T (phase 2), mirroring `while t < T` of the reference per path.
-    auto iteration = [&](float zs, auto checked, auto masked, int& k, float& x_at_n) {
+    auto iteration = [&](float r2, float cs, auto checked, auto masked, int& k, float& x_at_n) {
       if (decltype(checked)::value) {
         if (q >= q_end) {
           tau_acc = queue_refill<MARKS, true>(qdepth, chunk, plo, phi, tau_acc);
@@ -70,11 +74,13 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
       const bool active = decltype(masked)::value ? (t < T && k < kcap) : true;
       const float2 e = lds_float2(q);  // (tau, c J)
       const float dt = fmaxf(fminf(h0, fminf(e.x, T) - t), 0.0f);
-      const float sq = fast_sqrt(dt);
-      const float g = fmaf(sq, zs, a * dt);
+      // sigma z sqrt(dt) = sqrt(sigma^2 (-2 ln u) dt) * (cos | sin): the Box-Muller root and sqrt(dt) are one MUFU
+      const float g = fmaf(fast_sqrt(r2 * dt), cs, a * dt);
       const float xn = GEO ? fmaf(x, g, x) : x + g;
       t += dt;
-      bool hit = fabsf(e.x - t) <= fmaf(fabsf(t), 1e-5f, 1e-12f);
+      // torch.isclose(tau, t, atol=1e-12) with its default rtol=1e-5 (:212,225).  t never exceeds tau by more than
+      // an ulp (dt <= tau - t), so |tau - t| <= 1e-12 + 1e-5 |t|  <=>  t (1 + 1e-5) + 1e-12 >= tau.
+      bool hit = fmaf(t, 1.00001f, 1e-12f) >= e.x;
       if (decltype(masked)::value) hit = hit && active;
       const float Jc = hit ? e.y : 0.0f;
       if (GEO) x = fmaf(EXACT ? xn : x, Jc, xn);
@@ -85,15 +91,17 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
         if (active && k == n) x_at_n = x;
       }
     };
-    auto group_normals = [&](int b, float(&zs)[G]) {
+    // one Philox block -> squared radii (sigma^2 folded in) and directions of 6 normals; normal 2j uses
+    // (r2[j], cos), normal 2j+1 uses (r2[j], sin)
+    auto group_normals = [&](int b, float(&r2)[3], float(&cs)[G]) {
       uint32_t o[4];
       philox4x32_10((uint32_t)b, STREAM_DIFFUSION, plo, phi, keys, o);
-      float r[3], c[3], sn[3];
-      philox_polar3(o, neg2ln2_b2, r, c, sn);
+      float c[3], sn[3];
+      philox_polar3_sq(o, neg2ln2_b2, r2, c, sn);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        zs[2 * j] = r[j] * c[j];
-        zs[2 * j + 1] = r[j] * sn[j];
+        cs[2 * j] = c[j];
+        cs[2 * j + 1] = sn[j];
       }
     };
 
@@ -103,19 +111,19 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
     float x_at_n = x;
     const int nb_full = n / G;
     for (int b = 0; b < nb_full; ++b) {
-      float zs[G];
-      group_normals(b, zs);
+      float r2[3], cs[G];
+      group_normals(b, r2, cs);
       const float xs = x, ts = t;
       const uint32_t qs = q;
 #pragma unroll
-      for (int sp = 0; sp < G; ++sp) iteration(zs[sp], std::false_type(), std::false_type(), k, x_at_n);
+      for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::false_type(), std::false_type(), k, x_at_n);
       if (q >= q_end) {  // ran out of queued jumps inside the group: replay it with the refill test
         x = xs;
         t = ts;
         q = qs;
-        group_normals(b, zs);  // recomputed rather than kept live across the speculative group
+        group_normals(b, r2, cs);  // recomputed rather than kept live across the speculative group
 #pragma unroll
-        for (int sp = 0; sp < G; ++sp) iteration(zs[sp], std::true_type(), std::false_type(), k, x_at_n);
+        for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::true_type(), std::false_type(), k, x_at_n);
         if (q >= q_end) {  // the next group must start on a valid head
           tau_acc = queue_refill<MARKS, true>(qdepth, chunk, plo, phi, tau_acc);
           ++chunk;
@@ -127,10 +135,10 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
     if (k == n) x_at_n = x;
     // phase 2: the remaining num_steps % 6 iterations and those forced by jumps, until t reaches T
     for (int b = nb_full; t < T && k < kcap; ++b) {
-      float zs[G];
-      group_normals(b, zs);
+      float r2[3], cs[G];
+      group_normals(b, r2, cs);
 #pragma unroll
-      for (int sp = 0; sp < G; ++sp) iteration(zs[sp], std::true_type(), std::true_type(), k, x_at_n);
+      for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::true_type(), std::true_type(), k, x_at_n);
     }
 
     float xp[kMaxDim];

@@ -117,6 +117,22 @@ __device__ __forceinline__ void philox_polar3(const uint32_t (&o)[4], float neg2
     s[j] = fast_sin(ang);
   }
 }
+// same, without the square root: r2[j] = neg2ln2_scale2 * log2(u_j) is the SQUARED radius, for callers that fold a
+// per-use factor into it before taking the root (sqrt(r2 * dt) = radius * sqrt(dt): one MUFU instead of two)
+__device__ __forceinline__ void philox_polar3_sq(const uint32_t (&o)[4], float neg2ln2_scale2, float (&r2)[3],
+                                                 float (&c)[3], float (&s)[3]) {
+  const float f0 = angle_bits_to_12(o[3]);
+  const float f1 = __uint_as_float((o[3] >> 16) | 0x3f800000u);
+  const float f2 = angle_bits_to_12(__byte_perm(o[0], o[1], 0x0073));
+  const float fa[3] = {f0, f1, f2};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    r2[j] = fast_lg2(bits_to_u01_open0(o[j])) * neg2ln2_scale2;
+    const float ang = fmaf(fa[j], 804.247719318987f, -804.247719318987f);
+    c[j] = fast_cos(ang);
+    s[j] = fast_sin(ang);
+  }
+}
 // six unit normals in slot order (r0 c0, r0 s0, r1 c1, r1 s1, r2 c2, r2 s2)
 __device__ __forceinline__ void philox_normals6(const uint32_t (&o)[4], float* n) {
   float r[3], c[3], s[3];
