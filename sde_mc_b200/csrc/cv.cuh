@@ -4,14 +4,19 @@
 // ~20 B per path-step through HBM) -> apply_adapted_control_variates varred.py:98-131 (two MLP forwards over
 // bs*S rows), resp. the diffusion variant varred.py:75-95.
 //
-// Tensor cores (tcgen05, accumulators in TMEM): a CTA of 128 threads owns a tile of 128 paths; thread r is path r
-// is row r of every activation matrix and lane r of the TMEM accumulators.  Each time step evaluates both nets
+// Tensor cores (tcgen05, accumulators in TMEM): a CTA of 256 threads owns TWO tiles of 128 paths; path r of a tile is
+// row r of its activation matrices and lane r of its TMEM accumulators.  Warps 0-3 own (simulate) the paths of tile
+// 0, warps 4-7 those of tile 1; in the epilogues every row is shared by the two warps of its TMEM lane quadrant,
+// 32 accumulator columns each.  Each time step evaluates
 //   Linear(2,H) ReLU Linear(H,H) ReLU Linear(H,H) ReLU Linear(H,1)         (nets.py:39-93, BN-free, H <= 63)
-// as three rounds of tcgen05.mma (M=128, N=64, K=16|64, bf16 in / fp32 accumulate) whose A operand the threads
-// write themselves into shared memory in the canonical K-major no-swizzle UMMA layout, plus a SIMT dot product for
-// the last layer.  Biases are folded into the contraction: every padded activation vector carries a constant 1 in
-// slot 63 (W[n][63] = b[n], W[63][63] = 1).  The inputs (t, x) are split into bf16 hi + lo parts (two K slots each
-// with the same weight) so the nets are evaluated at fp32-accurate inputs; weights and hidden activations are bf16.
+// for both nets as FOUR rounds of tcgen05.mma per tile (M=128; N=64,K=16 | N=64,K=64 | N=64,K=64 | N=16,K=64; bf16
+// in, fp32 accumulate) whose A operand the threads write themselves into shared memory in the canonical K-major
+// no-swizzle UMMA layout.  The two tiles are software-pipelined against each other: while the tensor core runs
+// round r of one tile, the threads run the epilogue of the other tile (TMEM -> ReLU -> bf16 -> next A operand), so
+// MMA latency, commit/mbarrier latency and the CTA barrier of one tile hide behind SIMT work of the other.
+// Biases are folded into the contraction: every padded activation vector carries a constant 1 in slot 63
+// (W[n][63] = b[n], W[63][63] = 1).  The inputs (t, x) are split into bf16 hi + lo parts (two K slots each with the
+// same weight) so the nets are evaluated at fp32-accurate inputs; weights and hidden activations are bf16.
 // Any adapted f, g gives an unbiased estimator, so the reduced precision only perturbs the variance reduction.
 #pragma once
 #include <cuda_bf16.h>
@@ -27,13 +32,17 @@ struct DevMlp {
   int in_dim, hidden, out_dim;
 };
 
-constexpr int kCvThreads = 128;
+constexpr int kCvRows = 128;     // paths per tile = rows of the activation matrices = TMEM lanes
+constexpr int kCvThreads = 256;  // warps 0-3 own the paths of tile 0, warps 4-7 those of tile 1; all 8 share the epilogues
 constexpr int kCvOne = 63;  // index of the constant-one unit in every padded (64-wide) activation vector
 
 // shared-memory carve-up (bytes).  Operand tiles: 16-byte chunk c = k/8 of row r lives at c * (rows*16) + r * 16,
 // i.e. UMMA descriptors with LBO = rows*16 (K direction) and SBO = 128 (next group of 8 rows).
+constexpr int kCvTiles = 2;                 // path tiles per CTA, pipelined against each other
+constexpr int kCvHeadN = 16;                // N of the head MMA (smallest N for M = 128); only column 0 is used
 constexpr int kCvW1Bytes = 64 * 16 * 2;
 constexpr int kCvWBytes = 64 * 64 * 2;
+constexpr int kCvW4Bytes = kCvHeadN * 64 * 2;
 constexpr int kCvABytes = 128 * 64 * 2;
 constexpr int kCvOffW1F = 0;
 constexpr int kCvOffW1G = kCvOffW1F + kCvW1Bytes;
@@ -41,13 +50,13 @@ constexpr int kCvOffW2F = kCvOffW1G + kCvW1Bytes;
 constexpr int kCvOffW3F = kCvOffW2F + kCvWBytes;
 constexpr int kCvOffW2G = kCvOffW3F + kCvWBytes;
 constexpr int kCvOffW3G = kCvOffW2G + kCvWBytes;
-constexpr int kCvOffAF = kCvOffW3G + kCvWBytes;
-constexpr int kCvOffAG = kCvOffAF + kCvABytes;
-constexpr int kCvOffW4F = kCvOffAG + kCvABytes;  // fp32[64]
-constexpr int kCvOffW4G = kCvOffW4F + 256;
-constexpr int kCvOffBar = kCvOffW4G + 256;
-constexpr int kCvOffTmem = kCvOffBar + 8;
+constexpr int kCvOffW4F = kCvOffW3G + kCvWBytes;
+constexpr int kCvOffW4G = kCvOffW4F + kCvW4Bytes;
+constexpr int kCvOffA = kCvOffW4G + kCvW4Bytes;  // per tile: A_f then A_g
+constexpr int kCvOffBar = kCvOffA + kCvTiles * 2 * kCvABytes;
+constexpr int kCvOffTmem = kCvOffBar + 8 * kCvTiles;
 constexpr int kCvSmemBytes = kCvOffTmem + 8;
+constexpr int kCvTmemCols = 128 * kCvTiles;  // per tile: f accumulators in columns 0-63, g in 64-127
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -58,13 +67,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // cute::UMMA::InstrDescriptor for kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A and B,
 // N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kCvIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t cv_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(kCvIdesc), "r"(accumulate));
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -79,23 +91,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   }
 }
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
-      "%24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, "
-      "%46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]),
-        "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]),
-        "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]),
-        "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),
-        "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 // relu + round-to-nearest bf16 of two fp32 values in one instruction: low half <- lo, high half <- hi
 __device__ __forceinline__ uint32_t relu_pack_bf16x2(uint32_t lo_bits, uint32_t hi_bits) {
   uint32_t r;
@@ -105,31 +100,32 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(uint32_t lo_bits, uint32_t 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// epilogue of a hidden layer: this thread's 64 accumulator columns -> ReLU -> bf16 -> its row of the next A operand
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint32_t a_row_addr) {
-  uint32_t v[64];
-  tmem_ld64(taddr, v);
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// epilogue of a hidden layer, one half (32 accumulator columns) per thread: ReLU -> bf16 -> chunks 4*half .. 4*half+3
+// of this row of the next A operand.  taddr / a_row_addr already point at the half.
+__device__ __forceinline__ void hidden_epilogue_half(uint32_t taddr, uint32_t a_row_addr) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    sts128(a_row_addr + c * (128 * 16), relu_pack_bf16x2(v[8 * c + 0], v[8 * c + 1]),
+  for (int c = 0; c < 4; ++c) {
+    sts128(a_row_addr + c * (kCvRows * 16), relu_pack_bf16x2(v[8 * c + 0], v[8 * c + 1]),
            relu_pack_bf16x2(v[8 * c + 2], v[8 * c + 3]), relu_pack_bf16x2(v[8 * c + 4], v[8 * c + 5]),
            relu_pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
   }
 }
-// last layer on the SIMT pipes: sum_k w4[k] relu(h3[k]); slot 63 carries the bias (h3[63] == 1)
-__device__ __forceinline__ float head_epilogue(uint32_t taddr, const float* w4) {
-  uint32_t v[64];
-  tmem_ld64(taddr, v);
-  float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const float4 w = *reinterpret_cast<const float4*>(w4 + 4 * c);
-    acc0 = fmaf(w.x, fmaxf(__uint_as_float(v[4 * c + 0]), 0.0f), acc0);
-    acc1 = fmaf(w.y, fmaxf(__uint_as_float(v[4 * c + 1]), 0.0f), acc1);
-    acc0 = fmaf(w.z, fmaxf(__uint_as_float(v[4 * c + 2]), 0.0f), acc0);
-    acc1 = fmaf(w.w, fmaxf(__uint_as_float(v[4 * c + 3]), 0.0f), acc1);
-  }
-  return acc0 + acc1;
+// output of the head MMA: column 0 of this thread's accumulator row
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(v);
 }
 // first-layer A row: [t_hi, t_lo, x_hi, x_lo, 1, 0, 0, 0 | 0 x 8]
 __device__ __forceinline__ void write_input_row(uint32_t a_row_addr, float t, float x) {
@@ -142,7 +138,7 @@ __device__ __forceinline__ void write_input_row(uint32_t a_row_addr, float t, fl
 }
 
 // weights -> bf16 canonical operand tiles with folded biases (see header comment)
-__device__ __forceinline__ void load_mlp(const DevMlp& net, uint8_t* w1, uint8_t* w2, uint8_t* w3, float* w4) {
+__device__ __forceinline__ void load_mlp(const DevMlp& net, uint8_t* w1, uint8_t* w2, uint8_t* w3, uint8_t* w4) {
   const int H = net.hidden;
   for (int idx = threadIdx.x; idx < 64 * 16; idx += blockDim.x) {
     const int n = idx >> 4, k = idx & 15;
@@ -170,7 +166,13 @@ __device__ __forceinline__ void load_mlp(const DevMlp& net, uint8_t* w1, uint8_t
       *reinterpret_cast<__nv_bfloat16*>(dst + (k >> 3) * (64 * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(v);
     }
   }
-  for (int k = threadIdx.x; k < 64; k += blockDim.x) w4[k] = k < H ? net.w[3][k] : (k == kCvOne ? net.b[3][0] : 0.0f);
+  // head: B operand of kCvHeadN rows, row 0 = (w4, bias in the constant-one slot), the other rows zero
+  for (int idx = threadIdx.x; idx < kCvHeadN * 64; idx += blockDim.x) {
+    const int n = idx >> 6, k = idx & 63;
+    float v = 0.0f;
+    if (n == 0) v = k < H ? net.w[3][k] : (k == kCvOne ? net.b[3][0] : 0.0f);
+    *reinterpret_cast<__nv_bfloat16*>(w4 + (k >> 3) * (kCvHeadN * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(v);
+  }
 }
 
 struct DevCv {
@@ -188,20 +190,24 @@ __global__ void __launch_bounds__(kCvThreads) cv_kernel(const DevSde s, const De
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
   extern __shared__ __align__(1024) uint8_t cv_smem[];
   constexpr int MARKS = C::MARKS;
+  using Src = typename std::conditional<INJECT, InjectJumps<MARKS>, InlineJumps<MARKS>>::type;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int quad = warp & 3;        // TMEM lane quadrant this warp may access (lanes 32*quad .. 32*quad+31)
+  const int mine = warp >> 2;       // tile whose paths this thread owns; also the column half it converts
+  const int row = quad * 32 + (tid & 31);
   const uint32_t sbase = smem_u32(cv_smem);
-  const uint32_t bar = sbase + kCvOffBar;
-  const float* w4f = reinterpret_cast<const float*>(cv_smem + kCvOffW4F);
-  const float* w4g = reinterpret_cast<const float*>(cv_smem + kCvOffW4G);
 
-  load_mlp(f, cv_smem + kCvOffW1F, cv_smem + kCvOffW2F, cv_smem + kCvOffW3F, reinterpret_cast<float*>(cv_smem + kCvOffW4F));
-  if (JUMPS) load_mlp(g, cv_smem + kCvOffW1G, cv_smem + kCvOffW2G, cv_smem + kCvOffW3G, reinterpret_cast<float*>(cv_smem + kCvOffW4G));
+  load_mlp(f, cv_smem + kCvOffW1F, cv_smem + kCvOffW2F, cv_smem + kCvOffW3F, cv_smem + kCvOffW4F);
+  if (JUMPS) load_mlp(g, cv_smem + kCvOffW1G, cv_smem + kCvOffW2G, cv_smem + kCvOffW3G, cv_smem + kCvOffW4G);
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+#pragma unroll
+    for (int tl = 0; tl < kCvTiles; ++tl)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kCvOffBar + 8 * tl));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(sbase + kCvOffTmem));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kCvOffTmem),
+                 "n"(kCvTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -209,144 +215,199 @@ __global__ void __launch_bounds__(kCvThreads) cv_kernel(const DevSde s, const De
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *reinterpret_cast<const uint32_t*>(cv_smem + kCvOffTmem);
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
-  const uint32_t tacc_f = tlane, tacc_g = tlane + 64;           // f accumulators: columns 0-63, g: 64-127
-  const uint32_t a_row_f = sbase + kCvOffAF + tid * 16, a_row_g = sbase + kCvOffAG + tid * 16;
-  uint32_t phase = 0;
+  const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's 32 TMEM lanes
 
-  // one round: A operands are in place -> sync -> MMAs -> wait for their completion
-  auto mma_round = [&](int layer, int active_any_in, int* any_out) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my st.shared -> visible to the tensor core
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    const int any = __syncthreads_or(active_any_in);
-    if (any_out) *any_out = any;
-    if (!any) return;
+  // per-thread state of one path
+  struct Path {
+    float x, t, h, left, Jprev, cvsum;
+    float zbuf[4];
+    uint64_t i;
+    uint32_t plo, phi;
+    int own_iters;
+    bool valid, need_pop;
+    Src src;
+  };
+  Path p;
+  uint32_t phase[kCvTiles];
+  bool live[kCvTiles];
+#pragma unroll
+  for (int tl = 0; tl < kCvTiles; ++tl) phase[tl] = 0;
+  const int n = s.num_steps;
+  const int kcap = JUMPS ? (INJECT ? inj.K : 4 * (n + s.max_jumps) + 64) : n;
+
+  // tensor-core round r of tile tl (A operands in place, CTA barrier passed): one thread issues, everybody returns
+  auto issue_round = [&](int tl, int r) {
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int ksteps = layer == 0 ? 1 : 4;
-      const uint32_t wf = sbase + (layer == 0 ? kCvOffW1F : layer == 1 ? kCvOffW2F : kCvOffW3F);
-      const uint32_t wg = sbase + (layer == 0 ? kCvOffW1G : layer == 1 ? kCvOffW2G : kCvOffW3G);
+      const uint32_t acc = tmem + (uint32_t)tl * 128u;
+      const uint32_t af = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes), ag = af + kCvABytes;
+      const uint32_t wf = sbase + (r == 0 ? kCvOffW1F : r == 1 ? kCvOffW2F : r == 2 ? kCvOffW3F : kCvOffW4F);
+      const uint32_t wg = sbase + (r == 0 ? kCvOffW1G : r == 1 ? kCvOffW2G : r == 2 ? kCvOffW3G : kCvOffW4G);
+      const int ksteps = r == 0 ? 1 : 4;
+      const uint32_t brows = r == 3 ? kCvHeadN : 64;
+      const uint32_t idesc = r == 3 ? cv_idesc(kCvHeadN) : cv_idesc(64);
       for (int ks = 0; ks < ksteps; ++ks) {
-        umma_bf16(tmem, umma_desc(sbase + kCvOffAF + ks * 2 * (128 * 16), 128 * 16, 128),
-                  umma_desc(wf + ks * 2 * (64 * 16), 64 * 16, 128), ks > 0);
+        umma_bf16(acc, umma_desc(af + ks * 2 * (128 * 16), 128 * 16, 128),
+                  umma_desc(wf + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
         if (JUMPS)
-          umma_bf16(tmem + 64, umma_desc(sbase + kCvOffAG + ks * 2 * (128 * 16), 128 * 16, 128),
-                    umma_desc(wg + ks * 2 * (64 * 16), 64 * 16, 128), ks > 0);
+          umma_bf16(acc + 64, umma_desc(ag + ks * 2 * (128 * 16), 128 * 16, 128),
+                    umma_desc(wg + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
       }
-      umma_commit(bar);
+      umma_commit(sbase + kCvOffBar + 8 * tl);
     }
-    mbar_wait(bar, phase);
-    phase ^= 1u;
+  };
+  // my st.shared -> visible to the tensor core; my tcgen05.ld -> ordered before the next MMA; CTA barrier
+  auto round_barrier_or = [&](int pred) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    return __syncthreads_or(pred);
+  };
+  auto wait_round = [&](int tl) {
+    mbar_wait(sbase + kCvOffBar + 8 * tl, phase[tl]);
+    phase[tl] ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
+  auto t_input = [&](const Path& p, int k) {
+    return JUMPS ? p.t : (float)((double)s.T * (double)k / (double)n);  // partition(T, n, 'left')
+  };
+  auto is_active = [&](const Path& p, int k) { return p.valid && k < kcap && (JUMPS ? p.t < s.T : true); };
 
   Accum acc;
   acc.zero();
-  const uint64_t n_tiles = (rg.n_paths + kCvThreads - 1) / kCvThreads;
-  const int n = s.num_steps;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint64_t i = tile * kCvThreads + tid;
-    const bool valid = i < rg.n_paths;
-    const uint64_t gp = rg.path_lo + i;
-    const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
-    float x[kMaxDim], xo[kMaxDim];
+  const uint64_t n_tiles = (rg.n_paths + kCvRows - 1) / kCvRows;
+  for (uint64_t pair = blockIdx.x; pair * kCvTiles < n_tiles; pair += gridDim.x) {
+    // ---- start both tiles: state 0 -> first-layer operands -> round 0 in flight ------------------------------
+    p.i = (pair * kCvTiles + mine) * kCvRows + row;
+    p.valid = p.i < rg.n_paths;
+    {
+      const uint64_t gp = rg.path_lo + p.i;
+      p.plo = (uint32_t)gp;
+      p.phi = (uint32_t)(gp >> 32);
+    }
+    p.x = s.x0[0];
+    p.t = 0.0f;
+    p.h = s.h0;
+    p.left = s.x0[0];
+    p.Jprev = 0.0f;
+    p.cvsum = 0.0f;
+    p.own_iters = 0;
+    p.need_pop = true;
 #pragma unroll
-    for (int d = 0; d < kMaxDim; ++d) x[d] = d < 1 ? s.x0[d] : 0.0f;
-    float t = 0.0f, h = s.h0, left = s.x0[0], Jprev = 0.0f, cvsum = 0.0f;
-    bool need_pop = true;
-    typename std::conditional<INJECT, InjectJumps<MARKS>, InlineJumps<MARKS>>::type src;
+    for (int q = 0; q < 4; ++q) p.zbuf[q] = 0.0f;
     if constexpr (JUMPS) {
-      if constexpr (INJECT) src.init(s, inj, valid ? i : 0);
-      else src.init(plo, phi);
+      if constexpr (INJECT) p.src.init(s, inj, p.valid ? p.i : 0);
+      else p.src.init(p.plo, p.phi);
     }
-    const int kcap = JUMPS ? (INJECT ? inj.K : 4 * (n + s.max_jumps) + 64) : n;
-    float zbuf[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    int own_iters = 0;
-
-    for (int k = 0;; ++k) {
-      const bool active = valid && k < kcap && (JUMPS ? t < s.T : true);
-      // ---- both nets at the state of index k --------------------------------------------------------------
-      const float t_in = JUMPS ? t : (float)((double)s.T * (double)k / (double)n);  // partition(T, n, 'left')
-      write_input_row(a_row_f, t_in, x[0]);
-      if (JUMPS) write_input_row(a_row_g, t_in, left);
-      int any = 0;
-      mma_round(0, active ? 1 : 0, &any);
-      if (!any) break;
-      hidden_epilogue(tacc_f, a_row_f);
-      if (JUMPS) hidden_epilogue(tacc_g, a_row_g);
-      mma_round(1, 1, nullptr);
-      hidden_epilogue(tacc_f, a_row_f);
-      if (JUMPS) hidden_epilogue(tacc_g, a_row_g);
-      mma_round(2, 1, nullptr);
-      const float fval = head_epilogue(tacc_f, w4f);
-      const float gval = JUMPS ? head_epilogue(tacc_g, w4g) : 0.0f;
-
-      // ---- this thread's Brownian normal for iteration k (one Philox block serves 4 iterations) -----------
-      if ((k & 3) == 0) {
-        if constexpr (!INJECT) {
-          uint32_t o[4];
-          philox4x32_10((uint32_t)(k >> 2), STREAM_DIFFUSION, plo, phi, keys, o);
-          box_muller(o[0], o[1], zbuf[0], zbuf[1]);
-          box_muller(o[2], o[3], zbuf[2], zbuf[3]);
-        }
-      }
-      float z;
-      if constexpr (INJECT) {
-        z = (valid && k < inj.K) ? inj.z[i * (uint64_t)inj.K + k] : 0.0f;
-      } else {
-        z = zbuf[0];
-        zbuf[0] = zbuf[1]; zbuf[1] = zbuf[2]; zbuf[2] = zbuf[3];
-      }
-
-      // ---- advance the path by one iteration and accumulate the control variates -------------------------
-      if (active) {
-        const float D = fast_ex2(-t_in * cv.disc_rate_l2e);
-        float dt, sq;
-        float tau = 0.0f;
-        if constexpr (JUMPS) {
-          src.begin_iter(s, keys, k);
-          src.advance(s, keys, need_pop);
-          tau = src.tau;
-          h = fminf(h, fmaxf(s.T - t, 0.0f));
-          dt = fmaxf(fminf(h, tau - t), 0.0f);
-          sq = fast_sqrt(dt);
-        } else {
-          dt = s.h0;
-          sq = s.sqrt_h0;
-        }
-        const float dW = z * sq;
-        float w1[kMaxDim] = {z, 0.0f, 0.0f, 0.0f}, w2[kMaxDim] = {0.0f, 0.0f, 0.0f, 0.0f};
-        xo[0] = x[0];
-        euler_step<C>(s, x, dt, sq, w1, w2);
-        float c = fval * dW;                                     // f dW           (integrate_cv varred.py:202-214)
-        if constexpr (JUMPS) {
-          c = fmaf(gval, Jprev, c);                              // g J            (varred.py:124)
-          if (k < cv.last_interval) c = fmaf(cv.comp_c * gval, dt, c);   // - rate E[J] g dt (varred.py:126-127)
-          t += dt;
-          left = x[0];
-          const bool hit = fabsf(tau - t) <= fmaf(fabsf(t), 1e-5f, 1e-12f);
-          const float Jc = hit ? src.mark(s, k) : 0.0f;
-          if (s.exact_jumps) xo[0] = x[0];
-          add_jump<C>(s, x, xo, Jc);
-          Jprev = Jc;
-          need_pop = hit;
-        }
-        cvsum = fmaf(c, D, cvsum);
-        own_iters = k + 1;
-      }
+    const uint32_t my_row_f = sbase + kCvOffA + (uint32_t)mine * (2 * kCvABytes) + row * 16, my_row_g = my_row_f + kCvABytes;
+    write_input_row(my_row_f, t_input(p, 0), p.x);
+    if (JUMPS) write_input_row(my_row_g, t_input(p, 0), p.left);
+#pragma unroll
+    for (int tl = 0; tl < kCvTiles; ++tl) {
+      live[tl] = round_barrier_or((mine == tl && is_active(p, 0)) ? 1 : 0) != 0;
+      if (live[tl]) issue_round(tl, 0);
     }
 
-    if (valid) {
-      const float pay = eval_payoff<1>(po, x);
-      const float gamma = pay + cvsum;
-      if (cv.gamma_out) cv.gamma_out[i] = gamma;
-      acc.add(gamma, pay, own_iters);
+    for (int k = 0; live[0] || live[1]; ++k) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int tl = 0; tl < kCvTiles; ++tl) {
+          if (!live[tl]) continue;
+          const uint32_t tacc_f = tlane + (uint32_t)tl * 128u, tacc_g = tacc_f + 64;
+          const uint32_t a_row_f = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes) + row * 16, a_row_g = a_row_f + kCvABytes;
+          wait_round(tl);
+          if (r < 3) {
+            // hidden layer r+1: accumulators -> ReLU -> bf16 -> A operand of the next round; this thread converts
+            // columns 32*mine .. 32*mine+31 of its row, its partner warp (same quadrant) the other half
+            hidden_epilogue_half(tacc_f + 32 * mine, a_row_f + mine * 4 * (kCvRows * 16));
+            if (JUMPS) hidden_epilogue_half(tacc_g + 32 * mine, a_row_g + mine * 4 * (kCvRows * 16));
+            round_barrier_or(0);
+            issue_round(tl, r + 1);
+            continue;
+          }
+          if (mine != tl) {  // the owners of this tile advance their paths; everybody meets at the barrier
+            live[tl] = round_barrier_or(0) != 0;
+            if (live[tl]) issue_round(tl, 0);
+            continue;
+          }
+          // ---- r == 3: both nets evaluated at the state of index k -> advance the path by one iteration -------
+          const float fval = tmem_ld1(tacc_f);
+          const float gval = JUMPS ? tmem_ld1(tacc_g) : 0.0f;
+          const bool active = is_active(p, k);
+          const float t_in = t_input(p, k);
+          // this thread's Brownian normal for iteration k (one Philox block serves 4 iterations)
+          if ((k & 3) == 0) {
+            if constexpr (!INJECT) {
+              uint32_t o[4];
+              philox4x32_10((uint32_t)(k >> 2), STREAM_DIFFUSION, p.plo, p.phi, keys, o);
+              box_muller(o[0], o[1], p.zbuf[0], p.zbuf[1]);
+              box_muller(o[2], o[3], p.zbuf[2], p.zbuf[3]);
+            }
+          }
+          float z;
+          if constexpr (INJECT) {
+            z = (p.valid && k < inj.K) ? inj.z[p.i * (uint64_t)inj.K + k] : 0.0f;
+          } else {
+            z = p.zbuf[0];
+            p.zbuf[0] = p.zbuf[1]; p.zbuf[1] = p.zbuf[2]; p.zbuf[2] = p.zbuf[3];
+          }
+          if (active) {
+            const float D = fast_ex2(-t_in * cv.disc_rate_l2e);
+            float dt, sq;
+            float tau = 0.0f;
+            if constexpr (JUMPS) {
+              p.src.begin_iter(s, keys, k);
+              p.src.advance(s, keys, p.need_pop);
+              tau = p.src.tau;
+              p.h = fminf(p.h, fmaxf(s.T - p.t, 0.0f));
+              dt = fmaxf(fminf(p.h, tau - p.t), 0.0f);
+              sq = fast_sqrt(dt);
+            } else {
+              dt = s.h0;
+              sq = s.sqrt_h0;
+            }
+            const float dW = z * sq;
+            float xv[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f}, xo[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
+            float w1[kMaxDim] = {z, 0.0f, 0.0f, 0.0f}, w2[kMaxDim] = {0.0f, 0.0f, 0.0f, 0.0f};
+            euler_step<C>(s, xv, dt, sq, w1, w2);
+            float c = fval * dW;                                     // f dW           (integrate_cv varred.py:202-214)
+            if constexpr (JUMPS) {
+              c = fmaf(gval, p.Jprev, c);                            // g J            (varred.py:124)
+              if (k < cv.last_interval) c = fmaf(cv.comp_c * gval, dt, c);   // - rate E[J] g dt (varred.py:126-127)
+              p.t += dt;
+              p.left = xv[0];
+              const bool hit = fabsf(tau - p.t) <= fmaf(fabsf(p.t), 1e-5f, 1e-12f);
+              const float Jc = hit ? p.src.mark(s, k) : 0.0f;
+              if (s.exact_jumps) xo[0] = xv[0];
+              add_jump<C>(s, xv, xo, Jc);
+              p.Jprev = Jc;
+              p.need_pop = hit;
+            }
+            p.x = xv[0];
+            p.cvsum = fmaf(c, D, p.cvsum);
+            p.own_iters = k + 1;
+          }
+          // first-layer operands of state k+1, then round 0 of the next step (if any path of the tile goes on)
+          write_input_row(a_row_f, t_input(p, k + 1), p.x);
+          if (JUMPS) write_input_row(a_row_g, t_input(p, k + 1), p.left);
+          live[tl] = round_barrier_or(is_active(p, k + 1) ? 1 : 0) != 0;
+          if (live[tl]) issue_round(tl, 0);
+        }
+      }
+    }
+
+    if (p.valid) {
+      float xp[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
+      const float pay = eval_payoff<1>(po, xp);
+      const float gamma = pay + p.cvsum;
+      if (cv.gamma_out) cv.gamma_out[p.i] = gamma;
+      acc.add(gamma, pay, p.own_iters);
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kCvTmemCols));
   block_reduce_and_publish(acc, d_moments, d_ws);
 }
 

@@ -15,14 +15,16 @@ int run(Kernel kernel, const LaunchArgs& a, const DevMlp& f, const DevMlp& g, co
   SDEMC_CUDA_CHECK(cudaGetDevice(&dev));
   SDEMC_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  // (the occupancy API reports 1 here although three 72 KB CTAs fit in 227 KB and do co-reside: measured 2x)
+  // two CTAs per SM: 2 x ~105 KB of shared memory, 2 x 256 of the SM's 512 TMEM columns
+  // (the occupancy API under-reports co-residency of large-shared-memory CTAs here; measured)
   per_sm = (227 * 1024) / (kCvSmemBytes + 4096);
   if (const char* e = getenv("SDEMC_CV_CTAS_PER_SM")) per_sm = atoi(e);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;  // 128 TMEM columns per CTA, 512 per SM
+  if (per_sm > 512 / kCvTmemCols) per_sm = 512 / kCvTmemCols;
   uint64_t grid = (uint64_t)sms * per_sm;
-  const uint64_t tiles = (a.range.n_paths + kCvThreads - 1) / kCvThreads;
-  if (tiles < grid) grid = tiles;
+  const uint64_t tiles = (a.range.n_paths + kCvRows - 1) / kCvRows;
+  const uint64_t pairs = (tiles + kCvTiles - 1) / kCvTiles;
+  if (pairs < grid) grid = pairs;
   kernel<<<(unsigned)grid, kCvThreads, kCvSmemBytes, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, f, g, cv,
                                                                 a.d_moments, a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
