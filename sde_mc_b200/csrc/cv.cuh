@@ -33,7 +33,8 @@ struct DevMlp {
 };
 
 constexpr int kCvRows = 128;     // paths per tile = rows of the activation matrices = TMEM lanes
-constexpr int kCvThreads = 256;  // warps 0-3 own the paths of tile 0, warps 4-7 those of tile 1; all 8 share the epilogues
+constexpr int kCvWorkerWarps = 8; // warps 0-3 own the paths of tile 0, warps 4-7 those of tile 1; all 8 share the epilogues
+constexpr int kCvThreads = (kCvWorkerWarps + 1) * 32;  // + the MMA issuer warp
 constexpr int kCvOne = 63;  // index of the constant-one unit in every padded (64-wide) activation vector
 
 // shared-memory carve-up (bytes).  Operand tiles: 16-byte chunk c = k/8 of row r lives at c * (rows*16) + r * 16,
@@ -54,8 +55,9 @@ constexpr int kCvOffW4F = kCvOffW3G + kCvWBytes;
 constexpr int kCvOffW4G = kCvOffW4F + kCvW4Bytes;
 constexpr int kCvOffA = kCvOffW4G + kCvW4Bytes;  // per tile: A_f then A_g
 constexpr int kCvOffBar = kCvOffA + kCvTiles * 2 * kCvABytes;
-constexpr int kCvOffTmem = kCvOffBar + 8 * kCvTiles;
-constexpr int kCvSmemBytes = kCvOffTmem + 8;
+constexpr int kCvOffTmem = kCvOffBar + 16 * kCvTiles;  // full[tile] then done[tile]
+constexpr int kCvOffFlags = kCvOffTmem + 8;            // int any_active[tile][parity], int live[tile]
+constexpr int kCvSmemBytes = kCvOffFlags + 4 * 3 * kCvTiles + 8;
 constexpr int kCvTmemCols = 128 * kCvTiles;  // per tile: f accumulators in columns 0-63, g in 64-127
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -182,27 +184,50 @@ struct DevCv {
   float* gamma_out;     // (n) per-path gamma or nullptr
 };
 
+// ---- mbarrier helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // 1-D 'diag' SDE (dim == 1, m == 1): Merton-type jump diffusion (JUMPS) or GBM-type diffusion (!JUMPS)
+//
+// Warp roles: warps 0-7 are workers (warps 0-3 own the paths of tile 0, warps 4-7 those of tile 1; in the hidden-layer
+// epilogues every row is shared by the two warps of its TMEM lane quadrant, 32 accumulator columns each); warp 8 is
+// the MMA issuer (one thread).  Hand-off per tile is by two mbarriers, no CTA barrier in the loop:
+//   full[tl]  (256 arrivals)  workers -> issuer : the A operands of the next round are in shared memory
+//   done[tl]  (1 arrival)     issuer  -> workers: tcgen05.commit of that round's MMAs (or a plain arrive when the tile
+//                                                 has no active path left; tile_live[tl] says which)
+// Both sides walk the same (step, round, tile) sequence, so while the issuer and the tensor core work on one tile
+// the workers convert or advance the other.
 template <class C, bool JUMPS, bool INJECT>
-__global__ void __launch_bounds__(kCvThreads) cv_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+__global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                         const PhiloxKeys keys, const DevInject inj, const DevMlp f,
                                                         const DevMlp g, const DevCv cv,
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
   extern __shared__ __align__(1024) uint8_t cv_smem[];
   constexpr int MARKS = C::MARKS;
-  using Src = typename std::conditional<INJECT, InjectJumps<MARKS>, InlineJumps<MARKS>>::type;
+  using Src = typename std::conditional<INJECT, InjectJumps<MARKS>, LazyJumps<MARKS>>::type;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool worker = warp < kCvWorkerWarps;
   const int quad = warp & 3;        // TMEM lane quadrant this warp may access (lanes 32*quad .. 32*quad+31)
-  const int mine = warp >> 2;       // tile whose paths this thread owns; also the column half it converts
+  const int mine = (warp >> 2) & 1; // tile whose paths this thread owns; also the column half it converts
   const int row = quad * 32 + (tid & 31);
   const uint32_t sbase = smem_u32(cv_smem);
+  const uint32_t bar_full = sbase + kCvOffBar, bar_done = bar_full + 8 * kCvTiles;
+  volatile int* flags = reinterpret_cast<volatile int*>(cv_smem + kCvOffFlags);  // [tile][parity] any-active, then live[tile]
 
   load_mlp(f, cv_smem + kCvOffW1F, cv_smem + kCvOffW2F, cv_smem + kCvOffW3F, cv_smem + kCvOffW4F);
   if (JUMPS) load_mlp(g, cv_smem + kCvOffW1G, cv_smem + kCvOffW2G, cv_smem + kCvOffW3G, cv_smem + kCvOffW4G);
   if (tid == 0) {
 #pragma unroll
-    for (int tl = 0; tl < kCvTiles; ++tl)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbase + kCvOffBar + 8 * tl));
+    for (int tl = 0; tl < kCvTiles; ++tl) {
+      mbar_init(bar_full + 8 * tl, kCvWorkerWarps * 32);
+      mbar_init(bar_done + 8 * tl, 1);
+    }
+    for (int q = 0; q < 3 * kCvTiles; ++q) flags[q] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   if (warp == 0) {
@@ -217,191 +242,232 @@ __global__ void __launch_bounds__(kCvThreads) cv_kernel(const DevSde s, const De
   const uint32_t tmem = *reinterpret_cast<const uint32_t*>(cv_smem + kCvOffTmem);
   const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's 32 TMEM lanes
 
-  // per-thread state of one path
-  struct Path {
-    float x, t, h, left, Jprev, cvsum;
-    float zbuf[4];
-    uint64_t i;
-    uint32_t plo, phi;
-    int own_iters;
-    bool valid, need_pop;
-    Src src;
-  };
-  Path p;
-  uint32_t phase[kCvTiles];
-  bool live[kCvTiles];
-#pragma unroll
-  for (int tl = 0; tl < kCvTiles; ++tl) phase[tl] = 0;
   const int n = s.num_steps;
   const int kcap = JUMPS ? (INJECT ? inj.K : 4 * (n + s.max_jumps) + 64) : n;
-
-  // tensor-core round r of tile tl (A operands in place, CTA barrier passed): one thread issues, everybody returns
-  auto issue_round = [&](int tl, int r) {
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t acc = tmem + (uint32_t)tl * 128u;
-      const uint32_t af = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes), ag = af + kCvABytes;
-      const uint32_t wf = sbase + (r == 0 ? kCvOffW1F : r == 1 ? kCvOffW2F : r == 2 ? kCvOffW3F : kCvOffW4F);
-      const uint32_t wg = sbase + (r == 0 ? kCvOffW1G : r == 1 ? kCvOffW2G : r == 2 ? kCvOffW3G : kCvOffW4G);
-      const int ksteps = r == 0 ? 1 : 4;
-      const uint32_t brows = r == 3 ? kCvHeadN : 64;
-      const uint32_t idesc = r == 3 ? cv_idesc(kCvHeadN) : cv_idesc(64);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        umma_bf16(acc, umma_desc(af + ks * 2 * (128 * 16), 128 * 16, 128),
-                  umma_desc(wf + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
-        if (JUMPS)
-          umma_bf16(acc + 64, umma_desc(ag + ks * 2 * (128 * 16), 128 * 16, 128),
-                    umma_desc(wg + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
-      }
-      umma_commit(sbase + kCvOffBar + 8 * tl);
-    }
-  };
-  // my st.shared -> visible to the tensor core; my tcgen05.ld -> ordered before the next MMA; CTA barrier
-  auto round_barrier_or = [&](int pred) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    return __syncthreads_or(pred);
-  };
-  auto wait_round = [&](int tl) {
-    mbar_wait(sbase + kCvOffBar + 8 * tl, phase[tl]);
-    phase[tl] ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  };
-  auto t_input = [&](const Path& p, int k) {
-    return JUMPS ? p.t : (float)((double)s.T * (double)k / (double)n);  // partition(T, n, 'left')
-  };
-  auto is_active = [&](const Path& p, int k) { return p.valid && k < kcap && (JUMPS ? p.t < s.T : true); };
-
+  const uint64_t n_tiles = (rg.n_paths + kCvRows - 1) / kCvRows;
   Accum acc;
   acc.zero();
-  const uint64_t n_tiles = (rg.n_paths + kCvRows - 1) / kCvRows;
-  for (uint64_t pair = blockIdx.x; pair * kCvTiles < n_tiles; pair += gridDim.x) {
-    // ---- start both tiles: state 0 -> first-layer operands -> round 0 in flight ------------------------------
-    p.i = (pair * kCvTiles + mine) * kCvRows + row;
-    p.valid = p.i < rg.n_paths;
-    {
-      const uint64_t gp = rg.path_lo + p.i;
-      p.plo = (uint32_t)gp;
-      p.phi = (uint32_t)(gp >> 32);
-    }
-    p.x = s.x0[0];
-    p.t = 0.0f;
-    p.h = s.h0;
-    p.left = s.x0[0];
-    p.Jprev = 0.0f;
-    p.cvsum = 0.0f;
-    p.own_iters = 0;
-    p.need_pop = true;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) p.zbuf[q] = 0.0f;
-    if constexpr (JUMPS) {
-      if constexpr (INJECT) p.src.init(s, inj, p.valid ? p.i : 0);
-      else p.src.init(p.plo, p.phi);
-    }
-    const uint32_t my_row_f = sbase + kCvOffA + (uint32_t)mine * (2 * kCvABytes) + row * 16, my_row_g = my_row_f + kCvABytes;
-    write_input_row(my_row_f, t_input(p, 0), p.x);
-    if (JUMPS) write_input_row(my_row_g, t_input(p, 0), p.left);
-#pragma unroll
-    for (int tl = 0; tl < kCvTiles; ++tl) {
-      live[tl] = round_barrier_or((mine == tl && is_active(p, 0)) ? 1 : 0) != 0;
-      if (live[tl]) issue_round(tl, 0);
-    }
 
-    for (int k = 0; live[0] || live[1]; ++k) {
+  if (!worker) {
+    // ================================ MMA issuer (one thread of warp 8) ========================================
+    if (tid == kCvWorkerWarps * 32) {
+      uint32_t ph_full[kCvTiles] = {0, 0};
+      auto issue = [&](int tl, int r) {
+        const uint32_t accum = tmem + (uint32_t)tl * 128u;
+        const uint32_t af = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes), ag = af + kCvABytes;
+        const uint32_t wf = sbase + (r == 0 ? kCvOffW1F : r == 1 ? kCvOffW2F : r == 2 ? kCvOffW3F : kCvOffW4F);
+        const uint32_t wg = sbase + (r == 0 ? kCvOffW1G : r == 1 ? kCvOffW2G : r == 2 ? kCvOffW3G : kCvOffW4G);
+        const int ksteps = r == 0 ? 1 : 4;
+        const uint32_t brows = r == 3 ? kCvHeadN : 64;
+        const uint32_t idesc = r == 3 ? cv_idesc(kCvHeadN) : cv_idesc(64);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          umma_bf16(accum, umma_desc(af + ks * 2 * (128 * 16), 128 * 16, 128),
+                    umma_desc(wf + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
+          if (JUMPS)
+            umma_bf16(accum + 64, umma_desc(ag + ks * 2 * (128 * 16), 128 * 16, 128),
+                      umma_desc(wg + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
+        }
+        umma_commit(bar_done + 8 * tl);
+      };
+      // round 0 of a step starts only if some path of the tile is still active (flag written by its owners)
+      auto start_step = [&](int tl, int par) -> bool {
+        mbar_wait(bar_full + 8 * tl, ph_full[tl]);
+        ph_full[tl] ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool any = flags[tl * 2 + par] != 0;
+        flags[tl * 2 + par] = 0;
+        flags[2 * kCvTiles + tl] = any ? 1 : 0;
+        __threadfence_block();  // flag writes before the arrival (commit or plain) the workers synchronise on
+        if (any) issue(tl, 0);
+        else mbar_arrive(bar_done + 8 * tl);
+        return any;
+      };
+      for (uint64_t pair = blockIdx.x; pair * kCvTiles < n_tiles; pair += gridDim.x) {
+        bool live[kCvTiles];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+        for (int tl = 0; tl < kCvTiles; ++tl) live[tl] = start_step(tl, 0);
+        for (int k = 0; live[0] || live[1]; ++k) {
 #pragma unroll
-        for (int tl = 0; tl < kCvTiles; ++tl) {
-          if (!live[tl]) continue;
-          const uint32_t tacc_f = tlane + (uint32_t)tl * 128u, tacc_g = tacc_f + 64;
-          const uint32_t a_row_f = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes) + row * 16, a_row_g = a_row_f + kCvABytes;
-          wait_round(tl);
-          if (r < 3) {
-            // hidden layer r+1: accumulators -> ReLU -> bf16 -> A operand of the next round; this thread converts
-            // columns 32*mine .. 32*mine+31 of its row, its partner warp (same quadrant) the other half
-            hidden_epilogue_half(tacc_f + 32 * mine, a_row_f + mine * 4 * (kCvRows * 16));
-            if (JUMPS) hidden_epilogue_half(tacc_g + 32 * mine, a_row_g + mine * 4 * (kCvRows * 16));
-            round_barrier_or(0);
-            issue_round(tl, r + 1);
-            continue;
-          }
-          if (mine != tl) {  // the owners of this tile advance their paths; everybody meets at the barrier
-            live[tl] = round_barrier_or(0) != 0;
-            if (live[tl]) issue_round(tl, 0);
-            continue;
-          }
-          // ---- r == 3: both nets evaluated at the state of index k -> advance the path by one iteration -------
-          const float fval = tmem_ld1(tacc_f);
-          const float gval = JUMPS ? tmem_ld1(tacc_g) : 0.0f;
-          const bool active = is_active(p, k);
-          const float t_in = t_input(p, k);
-          // this thread's Brownian normal for iteration k (one Philox block serves 4 iterations)
-          if ((k & 3) == 0) {
-            if constexpr (!INJECT) {
-              uint32_t o[4];
-              philox4x32_10((uint32_t)(k >> 2), STREAM_DIFFUSION, p.plo, p.phi, keys, o);
-              box_muller(o[0], o[1], p.zbuf[0], p.zbuf[1]);
-              box_muller(o[2], o[3], p.zbuf[2], p.zbuf[3]);
+          for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int tl = 0; tl < kCvTiles; ++tl) {
+              if (!live[tl]) continue;
+              if (r < 3) {
+                mbar_wait(bar_full + 8 * tl, ph_full[tl]);
+                ph_full[tl] ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue(tl, r + 1);
+              } else {
+                live[tl] = start_step(tl, (k + 1) & 1);
+              }
             }
           }
-          float z;
-          if constexpr (INJECT) {
-            z = (p.valid && k < inj.K) ? inj.z[p.i * (uint64_t)inj.K + k] : 0.0f;
-          } else {
-            z = p.zbuf[0];
-            p.zbuf[0] = p.zbuf[1]; p.zbuf[1] = p.zbuf[2]; p.zbuf[2] = p.zbuf[3];
-          }
-          if (active) {
-            const float D = fast_ex2(-t_in * cv.disc_rate_l2e);
-            float dt, sq;
-            float tau = 0.0f;
-            if constexpr (JUMPS) {
-              p.src.begin_iter(s, keys, k);
-              p.src.advance(s, keys, p.need_pop);
-              tau = p.src.tau;
-              p.h = fminf(p.h, fmaxf(s.T - p.t, 0.0f));
-              dt = fmaxf(fminf(p.h, tau - p.t), 0.0f);
-              sq = fast_sqrt(dt);
-            } else {
-              dt = s.h0;
-              sq = s.sqrt_h0;
-            }
-            const float dW = z * sq;
-            float xv[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f}, xo[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
-            float w1[kMaxDim] = {z, 0.0f, 0.0f, 0.0f}, w2[kMaxDim] = {0.0f, 0.0f, 0.0f, 0.0f};
-            euler_step<C>(s, xv, dt, sq, w1, w2);
-            float c = fval * dW;                                     // f dW           (integrate_cv varred.py:202-214)
-            if constexpr (JUMPS) {
-              c = fmaf(gval, p.Jprev, c);                            // g J            (varred.py:124)
-              if (k < cv.last_interval) c = fmaf(cv.comp_c * gval, dt, c);   // - rate E[J] g dt (varred.py:126-127)
-              p.t += dt;
-              p.left = xv[0];
-              const bool hit = fabsf(tau - p.t) <= fmaf(fabsf(p.t), 1e-5f, 1e-12f);
-              const float Jc = hit ? p.src.mark(s, k) : 0.0f;
-              if (s.exact_jumps) xo[0] = xv[0];
-              add_jump<C>(s, xv, xo, Jc);
-              p.Jprev = Jc;
-              p.need_pop = hit;
-            }
-            p.x = xv[0];
-            p.cvsum = fmaf(c, D, p.cvsum);
-            p.own_iters = k + 1;
-          }
-          // first-layer operands of state k+1, then round 0 of the next step (if any path of the tile goes on)
-          write_input_row(a_row_f, t_input(p, k + 1), p.x);
-          if (JUMPS) write_input_row(a_row_g, t_input(p, k + 1), p.left);
-          live[tl] = round_barrier_or(is_active(p, k + 1) ? 1 : 0) != 0;
-          if (live[tl]) issue_round(tl, 0);
         }
       }
     }
+  } else {
+    // ======================================== workers ==========================================================
+    struct Path {
+      float x, t, h, left, Jprev, cvsum;
+      float zbuf[4];
+      uint64_t i;
+      uint32_t plo, phi;
+      int own_iters;
+      bool valid, need_pop;
+      Src src;
+    };
+    Path p;
+    uint32_t ph_done[kCvTiles] = {0, 0};
+    auto t_input = [&](const Path& q, int k) {
+      return JUMPS ? q.t : (float)((double)s.T * (double)k / (double)n);  // partition(T, n, 'left')
+    };
+    auto is_active = [&](const Path& q, int k) { return q.valid && k < kcap && (JUMPS ? q.t < s.T : true); };
+    // my st.shared -> visible to the tensor core; my tcgen05.ld -> ordered before the next MMA; tell the issuer
+    auto operands_ready = [&](int tl) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_full + 8 * tl);
+    };
+    // round of tile tl finished?  returns false when the issuer retired the tile instead
+    auto wait_round = [&](int tl) -> bool {
+      mbar_wait(bar_done + 8 * tl, ph_done[tl]);
+      ph_done[tl] ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      return flags[2 * kCvTiles + tl] != 0;
+    };
+    const uint32_t my_row_f = sbase + kCvOffA + (uint32_t)mine * (2 * kCvABytes) + row * 16, my_row_g = my_row_f + kCvABytes;
 
-    if (p.valid) {
-      float xp[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
-      const float pay = eval_payoff<1>(po, xp);
-      const float gamma = pay + p.cvsum;
-      if (cv.gamma_out) cv.gamma_out[p.i] = gamma;
-      acc.add(gamma, pay, p.own_iters);
+    for (uint64_t pair = blockIdx.x; pair * kCvTiles < n_tiles; pair += gridDim.x) {
+      // ---- state 0 of my path -> first-layer operands of my tile ------------------------------------------------
+      p.i = (pair * kCvTiles + mine) * kCvRows + row;
+      p.valid = p.i < rg.n_paths;
+      {
+        const uint64_t gp = rg.path_lo + p.i;
+        p.plo = (uint32_t)gp;
+        p.phi = (uint32_t)(gp >> 32);
+      }
+      p.x = s.x0[0];
+      p.t = 0.0f;
+      p.h = s.h0;
+      p.left = s.x0[0];
+      p.Jprev = 0.0f;
+      p.cvsum = 0.0f;
+      p.own_iters = 0;
+      p.need_pop = true;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) p.zbuf[q] = 0.0f;
+      if constexpr (JUMPS) {
+        if constexpr (INJECT) p.src.init(s, inj, p.valid ? p.i : 0);
+        else p.src.init(p.plo, p.phi);
+      }
+      write_input_row(my_row_f, t_input(p, 0), p.x);
+      if (JUMPS) write_input_row(my_row_g, t_input(p, 0), p.left);
+      if (is_active(p, 0)) flags[mine * 2 + 0] = 1;
+      bool live[kCvTiles];
+#pragma unroll
+      for (int tl = 0; tl < kCvTiles; ++tl) {
+        operands_ready(tl);
+        live[tl] = true;
+      }
+
+      for (int k = 0; live[0] || live[1]; ++k) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int tl = 0; tl < kCvTiles; ++tl) {
+            if (!live[tl]) continue;
+            const uint32_t tacc_f = tlane + (uint32_t)tl * 128u, tacc_g = tacc_f + 64;
+            const uint32_t a_row_f = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes) + row * 16, a_row_g = a_row_f + kCvABytes;
+            const bool ok = wait_round(tl);
+            if (r == 0 && !ok) {  // no active path was left in the tile: the issuer retired it
+              live[tl] = false;
+              continue;
+            }
+            if (r < 3) {
+              // hidden layer r+1: accumulators -> ReLU -> bf16 -> A operand of the next round; this thread converts
+              // columns 32*mine .. 32*mine+31 of its row, its partner warp (same quadrant) the other half
+              hidden_epilogue_half(tacc_f + 32 * mine, a_row_f + mine * 4 * (kCvRows * 16));
+              if (JUMPS) hidden_epilogue_half(tacc_g + 32 * mine, a_row_g + mine * 4 * (kCvRows * 16));
+              operands_ready(tl);
+              continue;
+            }
+            if (mine != tl) {  // the owners of this tile advance their paths
+              operands_ready(tl);
+              continue;
+            }
+            // ---- r == 3: both nets evaluated at the state of index k -> advance my path by one iteration --------
+            const float fval = tmem_ld1(tacc_f);
+            const float gval = JUMPS ? tmem_ld1(tacc_g) : 0.0f;
+            const bool active = is_active(p, k);
+            const float t_in = t_input(p, k);
+            // this thread's Brownian normal for iteration k (one Philox block serves 4 iterations)
+            if ((k & 3) == 0) {
+              if constexpr (!INJECT) {
+                uint32_t o[4];
+                philox4x32_10((uint32_t)(k >> 2), STREAM_DIFFUSION, p.plo, p.phi, keys, o);
+                box_muller(o[0], o[1], p.zbuf[0], p.zbuf[1]);
+                box_muller(o[2], o[3], p.zbuf[2], p.zbuf[3]);
+              }
+            }
+            float z;
+            if constexpr (INJECT) {
+              z = (p.valid && k < inj.K) ? inj.z[p.i * (uint64_t)inj.K + k] : 0.0f;
+            } else {
+              z = p.zbuf[0];
+              p.zbuf[0] = p.zbuf[1]; p.zbuf[1] = p.zbuf[2]; p.zbuf[2] = p.zbuf[3];
+            }
+            if (active) {
+              const float D = fast_ex2(-t_in * cv.disc_rate_l2e);
+              float dt, sq;
+              float tau = 0.0f;
+              if constexpr (JUMPS) {
+                p.src.begin_iter(s, keys, k);
+                p.src.advance(s, keys, p.need_pop);
+                tau = p.src.tau;
+                p.h = fminf(p.h, fmaxf(s.T - p.t, 0.0f));
+                dt = fmaxf(fminf(p.h, tau - p.t), 0.0f);
+                sq = fast_sqrt(dt);
+              } else {
+                dt = s.h0;
+                sq = s.sqrt_h0;
+              }
+              const float dW = z * sq;
+              float xv[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f}, xo[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
+              float w1[kMaxDim] = {z, 0.0f, 0.0f, 0.0f}, w2[kMaxDim] = {0.0f, 0.0f, 0.0f, 0.0f};
+              euler_step<C>(s, xv, dt, sq, w1, w2);
+              float c = fval * dW;                                     // f dW           (integrate_cv varred.py:202-214)
+              if constexpr (JUMPS) {
+                c = fmaf(gval, p.Jprev, c);                            // g J            (varred.py:124)
+                if (k < cv.last_interval) c = fmaf(cv.comp_c * gval, dt, c);   // - rate E[J] g dt (varred.py:126-127)
+                p.t += dt;
+                p.left = xv[0];
+                const bool hit = fabsf(tau - p.t) <= fmaf(fabsf(p.t), 1e-5f, 1e-12f);
+                const float Jc = hit ? p.src.mark(s, k) : 0.0f;
+                if (s.exact_jumps) xo[0] = xv[0];
+                add_jump<C>(s, xv, xo, Jc);
+                p.Jprev = Jc;
+                p.need_pop = hit;
+              }
+              p.x = xv[0];
+              p.cvsum = fmaf(c, D, p.cvsum);
+              p.own_iters = k + 1;
+            }
+            // first-layer operands of state k+1; the issuer starts the next step if any path of the tile goes on
+            write_input_row(a_row_f, t_input(p, k + 1), p.x);
+            if (JUMPS) write_input_row(a_row_g, t_input(p, k + 1), p.left);
+            if (is_active(p, k + 1)) flags[tl * 2 + ((k + 1) & 1)] = 1;
+            operands_ready(tl);
+          }
+        }
+      }
+
+      if (p.valid) {
+        float xp[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
+        const float pay = eval_payoff<1>(po, xp);
+        const float gamma = pay + p.cvsum;
+        if (cv.gamma_out) cv.gamma_out[p.i] = gamma;
+        acc.add(gamma, pay, p.own_iters);
+      }
     }
   }
 

@@ -163,6 +163,35 @@ struct InlineJumps {
   __device__ __forceinline__ float mark(const DevSde&, int) const { return J; }
 };
 
+// Sparse jumps without a queue (fused control-variate kernel, whose shared memory is taken by operand tiles): the
+// next (gap, mark) pair is drawn only when the previous jump has been consumed -- a divergent branch, but with
+// rate * h << 1 most warp iterations skip it.  Counter = index of the jump, so the stream is independent of the grid.
+template <int MARKS>
+struct LazyJumps {
+  uint32_t plo, phi, njumps;
+  float tau, J;
+  __device__ __forceinline__ void init(uint32_t plo_, uint32_t phi_) {
+    plo = plo_;
+    phi = phi_;
+    njumps = 0;
+    tau = 0.0f;
+    J = 0.0f;
+  }
+  __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys&, int) {}
+  __device__ __forceinline__ void advance(const DevSde& s, const PhiloxKeys& keys, bool pop) {
+    if (pop) {
+      uint32_t o[4];
+      philox4x32_10(njumps++, STREAM_JUMP_INLINE, plo, phi, keys, o);
+      tau = fmaf(exp1_from_bits(o[0]), s.inv_rate, tau);
+      float raw, unused;
+      if (MARKS == SDEMC_MARKS_LOGNORMAL) box_muller(o[1], o[2], raw, unused);
+      else raw = bits_to_u01(o[1]);
+      J = mark_from_raw<MARKS>(s, raw);
+    }
+  }
+  __device__ __forceinline__ float mark(const DevSde&, int) const { return J; }
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // per-path state and one loop iteration
 // ------------------------------------------------------------------------------------------------------------
