@@ -45,7 +45,13 @@ WORKLOADS.update({
     "merton_store": dict(name="merton_1d_solve_full_storage_2e6x100", num_steps=100, paths=2 * 10 ** 6,
                          cpu_paths=10 ** 5),
 })
-OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0})
+WORKLOADS.update({
+    # configs[4]: MLMC Merton 1-D, coupled fine/coarse levels 1..128, allocation of mlmc.py:77-97 at eps = 1e-4
+    "mlmc": dict(name="merton_1d_mlmc_levels_1_2_4_to_128_eps1e-4", num_steps=1, paths=1, cpu_paths=1),
+})
+MLMC_LEVELS = [1, 2, 4, 8, 16, 32, 64, 128]
+MLMC_EPS = 1e-4
+OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0, "mlmc": 40.0})
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 
 
@@ -71,6 +77,11 @@ def build_problem(sm, workload, device):
         sde = sm.LevySde(levy, torch.tensor([1., 1.]))
         return sm.JumpEulerSolver(sde, 3, 256, device=device), sm.Rainbow(1.0), sm.ConstantShortRate(0.02), "adapted", None
     sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    if workload == "mlmc":
+        # exact_jumps=True: the coupled pair then telescopes exactly (with the reference's default
+        # the level corrections carry a -1.4e-3 bias, larger than the 1e-4 target)
+        return (sm.JumpEulerSolver(sde, 3, 1, device=device, exact_jumps=True), sm.EuroCall(1.0),
+                sm.ConstantShortRate(0.02), "adapted", None)
     if workload == "merton_cv":
         torch.manual_seed(0)   # random-init weights of the experiments' architecture (no checkpoints offline)
         nets = [sm.Mlp(2, [50, 50, 50], 1, batch_norm=False, batch_norm_init=False, device=device).eval()
@@ -128,7 +139,21 @@ def cpu_reference(workload, steps, warmup, sample_paths=None):
     w = WORKLOADS[workload]
     n = int(sample_paths or w["cpu_paths"])
     torch.set_num_threads(os.cpu_count() or 1)
-    if workload == "gbm_store":
+    if workload == "mlmc":
+        # bounded sample: the fine path of every level at 1/2000 of the optimal allocation's shape (single-level
+        # simulation only -- the coarse partner and the coupling are left out, which flatters the CPU)
+        spec = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1).kernel_spec()
+        shape = [3.7e8, 4.2e7, 2.6e7, 1.5e7, 7.8e6, 4.1e6, 2.1e6, 1.0e6]
+        counts = [max(int(c / 2000), 64) for c in shape]
+        w = dict(w, num_steps=1)
+        n = sum(c * l for c, l in zip(counts, MLMC_LEVELS))
+
+        def run():
+            last = 0.0
+            for c, l in zip(counts, MLMC_LEVELS):
+                last = float(tp.jump_solve(spec, 3, l, c, low_storage=True)[0][:, -1].mean())
+            return last, 0.0, 0.0
+    elif workload == "gbm_store":
         spec = sm.Gbm(0.02, 0.3, torch.tensor([1.]), 1).kernel_spec()
         run = lambda: (float(tp.diffusion_solve(spec, 3, 252, n)[0][:, -1].mean()), 0.0, 0.0)
     elif workload == "merton_store":
@@ -212,6 +237,20 @@ def main():
     # ---- device-resident leg: inputs (a parameter struct + Philox key) are already on the device side ----
     storing = args.workload.endswith("_store")
     store_bytes = [0]
+    mlmc = args.workload == "mlmc"
+    mlmc_trials = None
+    if mlmc:
+        from sde_mc_b200 import mlmc as M
+        mlmc_trials = sm.get_optimal_trials(10 ** 5, MLMC_LEVELS, MLMC_EPS, solver, payoff, discounter)  # untimed pilot
+        paths = sum(int(nl) * lv for nl, lv in zip(mlmc_trials, MLMC_LEVELS))   # fine path-steps per pass
+        w = dict(w, num_steps=1)
+
+    def mlmc_step():
+        # all levels queued back to back (each rank 1/G of every level), moments stay on the device
+        pend = [M._level_moments(solver, payoff, discounter, mlmc_trials[0], MLMC_LEVELS[0], 0)]
+        for li in range(1, len(MLMC_LEVELS)):
+            pend.append(M._level_moments(solver, payoff, discounter, mlmc_trials[li], MLMC_LEVELS[li], MLMC_LEVELS[li - 1]))
+        return pend
 
     def store_step():
         # the solve() contract: trajectories in the reference's layouts, resident in HBM (each rank its own paths)
@@ -225,6 +264,8 @@ def main():
         # every rank: `paths` paths of its own global path-id range (weak scaling), then the 64-byte all-reduce
         if storing:
             return store_step()
+        if mlmc:
+            return mlmc_step()
         if nets is not None:
             return sm.mc_cv_fused(nets, solver, paths * world, payoff, discounter)
         return E.run_moments(solver, payoff, discounter, paths * world, index_mode)
@@ -247,7 +288,19 @@ def main():
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    if storing:
+    mlmc_result = None
+    if mlmc:
+        tot_mean, tot_var, tot_iters, tot_n = 0.0, 0.0, 0.0, 0.0
+        for nl, m in zip(mlmc_trials, mom):
+            r = m.read()
+            mean_l, se_l = E.mean_and_stderr(r["sum"], r["sumsq"], int(nl))
+            tot_mean += mean_l
+            tot_var += se_l * se_l
+            tot_iters += r["iters"]
+            tot_n += r["n"]
+        mlmc_result = {"mean": tot_mean, "stderr": tot_var ** 0.5}
+        result = {"sum": 0.0, "sumsq": 0.0, "n": tot_n, "iters": tot_iters}
+    elif storing:
         last = mom
         mom = None
         final = last[0][:, -1, 0].double()
@@ -265,6 +318,8 @@ def main():
         if storing:
             stats = store_step()
             stats = None
+        elif mlmc:
+            stats = sm.mc_multilevel(mlmc_trials, MLMC_LEVELS, solver, payoff, discounter)
         elif nets is not None:
             stats = sm.mc_apply_cvs(nets, solver, paths * world, payoff, discounter, sim_bs=10 ** 5, bs=2000)
         else:
@@ -331,6 +386,21 @@ def main():
             out["e2e"]["call"] = "solver.solve(bs=paths)  (trajectories stay on the device, as in the reference)"
             out["e2e"]["d2h_bytes_per_step"] = 0
             out["estimate"] = {"mean_terminal_state": result["sum"] / result["n"], "n": result["n"]}
+        if mlmc:
+            # world == 1: `paths` = fine path-steps of one pass; every rank simulates 1/G of each level (strong scaling)
+            out["scaling"] = "strong"
+            out["value"] = value / world
+            out["e2e"]["value"] = e2e / world
+            out["e2e"]["call"] = "sde_mc_b200.mc_multilevel(trials, levels, solver, payoff, discounter)"
+            out["e2e"]["d2h_bytes_per_step"] = 64 * len(MLMC_LEVELS)
+            out["gpu_launches"] = args.steps * len(MLMC_LEVELS)
+            out["config"].update({"levels": MLMC_LEVELS, "eps": MLMC_EPS, "trials_per_level": [int(v) for v in mlmc_trials],
+                                  "fine_path_steps_per_pass": paths, "exact_jumps": True,
+                                  "parallelism": "every level sharded over %d GPU(s), one 64-byte all-reduce per level" % world})
+            out["roofline"]["achieved"] = OPS_PER_PATH_STEP["mlmc"] * out["value"] / 1e12 / world
+            out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
+            out["estimate"] = {"mean": mlmc_result["mean"], "stderr": mlmc_result["stderr"], "closed_form": 0.26298121,
+                               "rmse_vs_closed_form": ((mlmc_result["mean"] - 0.26298121) ** 2 + mlmc_result["stderr"] ** 2) ** 0.5}
         if nets is not None:
             iters_per_s = result["iters"] / (dev_ms * 1e-3) * args.steps / world
             tf = CV_TENSOR_FLOP_PER_ITER * iters_per_s / 1e12
