@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, STORE ? SDEMC_DIFF_STORE_MINB : (INJECT ?
     }
 
     int b_first = 0;
-    if constexpr (FAST1D) {
+    if (FAST1D && !s.milstein) {
       // 1-D single-driver moments path (GBM / log-GBM): sigma sqrt(h) is folded into the Box-Muller radius and
       // full Philox blocks (6 steps) run without per-step predicates: 2 FFMA per step on top of the normal.
       const int nb_full = S / SPB;

@@ -20,6 +20,7 @@ constexpr int kBlock = 256;  // threads per CTA of the moments kernels
 // ------------------------------------------------------------------------------------------------------------
 struct DevSde {
   int num_steps, max_jumps, exact_jumps;
+  int milstein;  // 1: Milstein correction 1/2 b b' (dW^2 - dt) on top of the Euler step (extension, 'diag' noise)
   float T, h0, sqrt_h0;
   float x0[kMaxDim];
   float chol[kMaxDim * kMaxDim];
@@ -140,6 +141,13 @@ __device__ __forceinline__ void euler_step(const DevSde& s, float (&x)[kMaxDim],
     float g = s.a[i] * dt;
     g = fmaf(s.b1[i] * sq, w1[i], g);
     if (C::M == 2) g = fmaf(s.b2[i] * sq, w2[i], g);
+    // Milstein (geometric: b b' = b1^2 x): + 1/2 b1^2 (dW^2 - dt) with dW = sq w, relative to x like the rest of g.
+    // Written on dW so that callers passing an accumulated increment (sq = 1, w = sum dW: the coarse path of an
+    // MLMC pair) get the right correction too.
+    if (C::M == 1 && C::FAMILY == SDEMC_FAMILY_GEOMETRIC && s.milstein) {
+      const float dw = sq * w1[i];
+      g = fmaf(0.5f * s.b1[i] * s.b1[i], fmaf(dw, dw, -dt), g);
+    }
     if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) x[i] = fmaf(x[i], g, x[i]);
     else x[i] += g;
   }
@@ -155,6 +163,8 @@ __device__ __forceinline__ void euler_step_uniform(const DevSde& s, float (&x)[k
   for (int i = 0; i < C::BASE; ++i) {
     float g = fmaf(s.b1s[i], w1[i], s.ah[i]);
     if (C::M == 2) g = fmaf(s.b2s[i], w2[i], g);
+    if (C::M == 1 && C::FAMILY == SDEMC_FAMILY_GEOMETRIC && s.milstein)
+      g = fmaf(0.5f * s.b1s[i] * s.b1s[i], fmaf(w1[i], w1[i], -1.0f), g);
     if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) x[i] = fmaf(x[i], g, x[i]);
     else x[i] += g;
   }

@@ -31,6 +31,7 @@ inline bool valid_sde(const sdemc_sde* s) {
   if (!(s->T > 0.0f)) return false;
   if (s->marks != SDEMC_MARKS_NONE && !(s->rate > 0.0f)) return false;
   if (s->asian && s->dim < 2) return false;
+  if (s->scheme == SDEMC_SCHEME_MILSTEIN && (s->m != 1 || s->family == SDEMC_FAMILY_HESTON)) return false;
   return true;
 }
 
@@ -41,6 +42,7 @@ inline DevSde to_dev(const sdemc_sde& s, int num_steps) {
   d.num_steps = num_steps;
   d.max_jumps = s.max_jumps;
   d.exact_jumps = s.exact_jumps;
+  d.milstein = s.scheme == SDEMC_SCHEME_MILSTEIN ? 1 : 0;
   d.T = s.T;
   d.h0 = (float)((double)s.T / (double)num_steps);
   d.sqrt_h0 = sqrtf(d.h0);

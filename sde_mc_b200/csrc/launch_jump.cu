@@ -42,7 +42,7 @@ int run_1d(const LaunchArgs& a) {
 template <class C>
 int by_mode(const LaunchArgs& a) {
   if constexpr (C::DIM == 1 && C::M == 1 && !C::ASIAN) {
-    if (!a.use_inject && !a.store && a.qdepth > 0)
+    if (!a.use_inject && !a.store && a.qdepth > 0 && !a.sde.milstein)
       return a.sde.exact_jumps ? run_1d<C, true>(a) : run_1d<C, false>(a);
   }
   if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;

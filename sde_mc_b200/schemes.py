@@ -25,3 +25,23 @@ class HestonScheme:
         root = solve_quadratic(self.sde.quadratic_parameters(x[:, 1], h, corr_normals[:, 1]))
         out[:, 1] = root * root
         return out
+
+
+class MilsteinScheme:
+    """Milstein: Euler + 1/2 b b' (dW^2 - h) for 'diag' noise.  EXTENSION -- the reference has no Milstein scheme
+    (SURVEY.md S3); validated by strong order 1 against the exact GBM solution.  The derivative b' is known for the
+    built-in families: geometric b = sigma x -> b' = sigma; arithmetic (constant b) -> b' = 0, i.e. Euler."""
+
+    def step(self, t, x, h, corr_normals):
+        if self.sde.diffusion_struct != 'diag':
+            raise NotImplementedError("Milstein is implemented for the 'diag' diffusion structure only")
+        b = self.sde.diffusion(t, x)
+        out = x + self.sde.drift(t, x) * h + b * corr_normals
+        spec = self.sde.kernel_spec()
+        from . import _lib as L
+        if spec.family == L.FAMILY_GEOMETRIC:
+            sigma = torch.tensor(spec.b1[:self.sde.dim], dtype=x.dtype, device=x.device)
+            if spec.asian:
+                sigma[-1] = 0.0
+            out = out + 0.5 * b * sigma * (corr_normals * corr_normals - h)
+        return out

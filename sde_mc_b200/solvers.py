@@ -15,7 +15,7 @@ from scipy.stats import poisson
 
 from . import _lib as L
 from . import _spec
-from .schemes import EulerScheme, HestonScheme
+from .schemes import EulerScheme, HestonScheme, MilsteinScheme
 
 
 def _alloc_rows(bs, inner_shape, dev, align):
@@ -86,6 +86,11 @@ class SdeSolver(ABC):
 
     def _sde_struct(self, num_steps=None):
         spec = _spec.spec_of(self.sde)
+        if isinstance(self, MilsteinScheme):
+            if spec.m != 1 or spec.family == L.FAMILY_HESTON:
+                raise L.SdemcError("the Milstein scheme is available for 'diag' geometric / arithmetic SDEs only")
+            import dataclasses
+            spec = dataclasses.replace(spec, scheme=L.SCHEME_MILSTEIN)
         return _spec.sde_struct(spec, self.time_interval, self.num_steps if num_steps is None else num_steps,
                                 self._max_jumps(), self._exact_jumps(), self.jump_strategy)
 
@@ -162,6 +167,11 @@ class EulerSolver(EulerScheme, DiffusionSolver):
 
 
 class HestonSolver(HestonScheme, DiffusionSolver):
+    pass
+
+
+class MilsteinSolver(MilsteinScheme, DiffusionSolver):
+    """Uniform-grid Milstein solver -- extension, not in the reference."""
     pass
 
 
@@ -257,6 +267,11 @@ class JumpDiffusionSolver(SdeSolver):
 
 
 class JumpEulerSolver(EulerScheme, JumpDiffusionSolver):
+    pass
+
+
+class JumpMilsteinSolver(MilsteinScheme, JumpDiffusionSolver):
+    """Jump-adapted solver with Milstein steps between the jumps -- extension, not in the reference."""
     pass
 
 

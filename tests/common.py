@@ -90,6 +90,9 @@ def jump_solver(name, g, device="cpu"):
 
 def oracle_sde(solver, num_steps=None):
     spec = solver.sde.kernel_spec()
+    if isinstance(solver, sm.MilsteinScheme):
+        import dataclasses
+        spec = dataclasses.replace(spec, scheme=2)
     return oracle.sde_struct(spec, solver.time_interval, solver.num_steps if num_steps is None else num_steps,
                              solver._max_jumps(), solver._exact_jumps())
 
