@@ -1,9 +1,67 @@
 // launch_diffusion.cu -- instantiation + dispatch of the uniform-grid kernels (diffusion.cuh)
+#include <cstdlib>
+
+#include <cudaTypedefs.h>
+
 #include "diffusion.cuh"
+#include "diffusion_tma.cuh"
 #include "launch.cuh"
 
 namespace sdemc {
 namespace {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+// (n_rows, row_len) fp32 array with `pitch` floats between rows -> 2-D tensor map with a [32 rows][32 elements]
+// box and the 128-byte swizzle of the staging tiles (diffusion_tma.cuh)
+bool make_row_map(CUtensorMap* map, float* base, uint64_t n_rows, uint64_t row_len, uint64_t pitch) {
+  auto encode = tensor_map_encoder();
+  if (!encode) return false;
+  const cuuint64_t dims[2] = {row_len, n_rows};
+  const cuuint64_t strides[1] = {pitch * sizeof(float)};
+  const cuuint32_t box[2] = {kTmaTileElems, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                kTmaTileElems == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
+inline bool tma_rows_ok(const float* base, uint64_t pitch) {
+  return base != nullptr && (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+}
+
+// path-storing launch through TMA (diffusion_tma.cuh); returns 1 when the layout does not qualify
+template <class C, bool HESTON, bool INJECT>
+int run_store_tma(const LaunchArgs& a) {
+  constexpr int NPS = C::BASE * C::M + (C::ASIAN ? 1 : 0);
+  if (!tma_rows_ok(a.out.paths, a.out.pitch_state) || !tma_rows_ok(a.out.normals, a.out.pitch_normals)) return 1;
+  if (a.range.n_paths >= (1ull << 31)) return 1;
+  if (getenv("SDEMC_NO_TMA_STORE")) return 1;
+  CUtensorMap mp, mn;
+  const uint64_t S = (uint64_t)a.sde.num_steps;
+  if (!make_row_map(&mp, a.out.paths, a.range.n_paths, (S + 1) * C::DIM, a.out.pitch_state)) return 1;
+  if (!make_row_map(&mn, a.out.normals, a.range.n_paths, S * NPS, a.out.pitch_normals)) return 1;
+  auto kernel = diffusion_store_tma_kernel<C, HESTON, INJECT>;
+  const size_t smem = (size_t)(kTmaStoreBlock / 32) * 4 * kTmaTileBytes + 1024;
+  SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = 0;
+  int rc = pick_grid(kernel, smem, a.range.n_paths, &grid, kTmaStoreBlock);
+  if (rc != SDEMC_OK) return rc;
+  kernel<<<grid, kTmaStoreBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, mp, mn);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
 
 template <class C, bool HESTON, bool INJECT, bool STORE>
 int run(const LaunchArgs& a) {
@@ -22,7 +80,12 @@ int run(const LaunchArgs& a) {
 
 template <class C, bool HESTON>
 int by_mode(const LaunchArgs& a) {
-  if (a.store) return a.use_inject ? run<C, HESTON, true, true>(a) : run<C, HESTON, false, true>(a);
+  if (a.store) {
+    // 16-byte aligned padded rows leave the SM through TMA; any other layout takes the store_tile.cuh kernel
+    const int rc = a.use_inject ? run_store_tma<C, HESTON, true>(a) : run_store_tma<C, HESTON, false>(a);
+    if (rc <= 0) return rc;
+    return a.use_inject ? run<C, HESTON, true, true>(a) : run<C, HESTON, false, true>(a);
+  }
   if (a.use_inject) return SDEMC_ERR_UNSUPPORTED;  // injected noise is only offered with stored outputs
   return run<C, HESTON, false, false>(a);
 }
