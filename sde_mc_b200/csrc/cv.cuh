@@ -20,6 +20,7 @@
 // Any adapted f, g gives an unbiased estimator, so the reduced precision only perturbs the variance reduction.
 #pragma once
 #include <cuda_bf16.h>
+#include <cstdio>
 
 #include "engine.cuh"
 #include "jump.cuh"
@@ -318,6 +319,14 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
     };
     Path p;
     uint32_t ph_done[kCvTiles] = {0, 0};
+#ifdef SDEMC_CV_PROFILE
+    long long prof_wait = 0, prof_epi = 0, prof_ready = 0, prof_adv = 0, prof_t0 = clock64(), prof_rounds = 0;
+#define CVP_BEGIN long long cvp_t = clock64();
+#define CVP_END(acc) { const long long cvp_n = clock64(); acc += cvp_n - cvp_t; cvp_t = cvp_n; }
+#else
+#define CVP_BEGIN
+#define CVP_END(acc)
+#endif
     auto t_input = [&](const Path& q, int k) {
       return JUMPS ? q.t : (float)((double)s.T * (double)k / (double)n);  // partition(T, n, 'left')
     };
@@ -378,7 +387,12 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
             if (!live[tl]) continue;
             const uint32_t tacc_f = tlane + (uint32_t)tl * 128u, tacc_g = tacc_f + 64;
             const uint32_t a_row_f = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes) + row * 16, a_row_g = a_row_f + kCvABytes;
+            CVP_BEGIN
             const bool ok = wait_round(tl);
+            CVP_END(prof_wait)
+#ifdef SDEMC_CV_PROFILE
+            ++prof_rounds;
+#endif
             if (r == 0 && !ok) {  // no active path was left in the tile: the issuer retired it
               live[tl] = false;
               continue;
@@ -388,7 +402,9 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
               // columns 32*mine .. 32*mine+31 of its row, its partner warp (same quadrant) the other half
               hidden_epilogue_half(tacc_f + 32 * mine, a_row_f + mine * 4 * (kCvRows * 16));
               if (JUMPS) hidden_epilogue_half(tacc_g + 32 * mine, a_row_g + mine * 4 * (kCvRows * 16));
+              CVP_END(prof_epi)
               operands_ready(tl);
+              CVP_END(prof_ready)
               continue;
             }
             if (mine != tl) {  // the owners of this tile advance their paths
@@ -456,7 +472,9 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
             write_input_row(a_row_f, t_input(p, k + 1), p.x);
             if (JUMPS) write_input_row(a_row_g, t_input(p, k + 1), p.left);
             if (is_active(p, k + 1)) flags[tl * 2 + ((k + 1) & 1)] = 1;
+            CVP_END(prof_adv)
             operands_ready(tl);
+            CVP_END(prof_ready)
           }
         }
       }
@@ -469,6 +487,12 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
         acc.add(gamma, pay, p.own_iters);
       }
     }
+#ifdef SDEMC_CV_PROFILE
+    if (blockIdx.x == 0 && (tid & 31) == 0)
+      printf("cvprof warp %d: total %lld clk, rounds %lld; per round: wait %.0f epi %.0f ready %.0f adv %.0f\n", warp,
+             clock64() - prof_t0, prof_rounds, (double)prof_wait / prof_rounds, (double)prof_epi / prof_rounds,
+             (double)prof_ready / prof_rounds, (double)prof_adv / prof_rounds);
+#endif
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
