@@ -87,16 +87,18 @@ constexpr int blocks_per_group(int nz) { return nz <= 3 ? 1 : (nz + kNormalsPerB
 // InverseCdf.__call__ levy.py:19-30 with lg2/ex2 on the XU pipe; pow(x, p) = ex2(p * lg2(x)).
 __device__ __forceinline__ float icdf_mark(const DevSde& s, float u) {
   const float y = u + s.ic_tol;  // levy.py:86
-  float r;
-  if (y <= s.ic_y1) {
-    r = fmaf(fast_lg2(s.ic_mulda_cm * y), s.ic_inv_mu_ln2, -1.0f);
-  } else if (y < s.ic_y2) {
-    r = -fast_ex2(s.ic_neg_inv_alpha * fast_lg2(fmaf(s.ic_alpha, fmaf(s.ic_lda_cm, y, -s.ic_inv_mu), 1.0f)));
-  } else if (y < s.ic_y3) {
-    r = fast_ex2(s.ic_neg_inv_alpha * fast_lg2(fmaf(s.ic_malpha_cp, fmaf(s.ic_lda, y, -s.ic_x3_off), s.ic_eps_ma)));
-  } else {
-    r = fmaf(-s.ic_inv_mu_ln2, fast_lg2(s.ic_mulda_cp * (1.0f - y)), 1.0f);
-  }
+  // The two power-law branches (|x| < 1: all but (c- + c+)/(mu lda) of the mass, < 1 % for the example models) are
+  // one expression with per-side constants, so a warp does not diverge on the sign of the jump ...
+  const bool right = !(y < s.ic_y2);
+  const float A = right ? s.ic_malpha_cp : s.ic_alpha;
+  const float Lc = right ? s.ic_lda : s.ic_lda_cm;
+  const float off = right ? s.ic_x3_off : s.ic_inv_mu;
+  const float B = right ? s.ic_eps_ma : 1.0f;
+  float r = fast_ex2(s.ic_neg_inv_alpha * fast_lg2(fmaf(A, fmaf(Lc, y, -off), B)));
+  r = right ? r : -r;
+  // ... and only the rare exponential tails branch
+  if (y <= s.ic_y1) r = fmaf(fast_lg2(s.ic_mulda_cm * y), s.ic_inv_mu_ln2, -1.0f);
+  else if (!(y < s.ic_y3)) r = fmaf(-s.ic_inv_mu_ln2, fast_lg2(s.ic_mulda_cp * (1.0f - y)), 1.0f);
   return r;
 }
 

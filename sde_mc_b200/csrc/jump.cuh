@@ -137,21 +137,33 @@ template <int MARKS>
 struct InlineJumps {
   uint32_t plo, phi;
   float tau, J, cand_gap, cand_raw;
+  float next_gap, next_raw;  // second (gap, mark) candidate of the current Philox block, for the odd iteration
   __device__ __forceinline__ void init(uint32_t plo_, uint32_t phi_) {
     plo = plo_;
     phi = phi_;
     tau = 0.0f;
     J = 0.0f;
+    next_gap = 0.0f;
+    next_raw = 0.0f;
   }
+  // one Philox block serves two consecutive iterations: (gap, mark) from words (0, 1) and (2, 3) for uniform
+  // marks; two gaps and one Box-Muller pair for lognormal marks.  k is the same for all active lanes of a warp.
   __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys& keys, int k) {
-    uint32_t o[4];
-    philox4x32_10((uint32_t)k, STREAM_JUMP_INLINE, plo, phi, keys, o);
-    cand_gap = exp1_from_bits(o[0]);
-    if (MARKS == SDEMC_MARKS_LOGNORMAL) {
-      float unused;
-      box_muller(o[1], o[2], cand_raw, unused);
+    if ((k & 1) == 0) {
+      uint32_t o[4];
+      philox4x32_10((uint32_t)(k >> 1), STREAM_JUMP_INLINE, plo, phi, keys, o);
+      cand_gap = exp1_from_bits(o[0]);
+      if (MARKS == SDEMC_MARKS_LOGNORMAL) {
+        next_gap = exp1_from_bits(o[1]);
+        box_muller(o[2], o[3], cand_raw, next_raw);
+      } else {
+        cand_raw = bits_to_u01(o[1]);
+        next_gap = exp1_from_bits(o[2]);
+        next_raw = bits_to_u01(o[3]);
+      }
     } else {
-      cand_raw = bits_to_u01(o[1]);
+      cand_gap = next_gap;
+      cand_raw = next_raw;
     }
   }
   __device__ __forceinline__ void advance(const DevSde& s, const PhiloxKeys&, bool pop) {
