@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
   } else {
     // ======================================== workers ==========================================================
     struct Path {
-      float x, t, h, left, Jprev, cvsum;
+      float x, t, left, Jprev, cvsum;
       float zbuf[4];
       uint64_t i;
       uint32_t plo, phi;
@@ -357,7 +357,6 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
       }
       p.x = s.x0[0];
       p.t = 0.0f;
-      p.h = s.h0;
       p.left = s.x0[0];
       p.Jprev = 0.0f;
       p.cvsum = 0.0f;
@@ -440,8 +439,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
                 p.src.begin_iter(s, keys, k);
                 p.src.advance(s, keys, p.need_pop);
                 tau = p.src.tau;
-                p.h = fminf(p.h, fmaxf(s.T - p.t, 0.0f));
-                dt = fmaxf(fminf(p.h, tau - p.t), 0.0f);
+                dt = fmaxf(fminf(s.h0, fminf(tau, s.T) - p.t), 0.0f);  // stateless mesh, see jump.cuh
                 sq = fast_sqrt(dt);
               } else {
                 dt = s.h0;

@@ -2,7 +2,7 @@
 //
 // Semantics kept from the reference loop:
 //   h  = min(h, max(T - t, 0))            the mesh only shrinks, the grid restarts at every jump   :190
-//   dt = min(h, tau - t)                                                                       :191
+//   dt = min(h, tau - t)                  evaluated statelessly as min(h0, min(tau, T) - t)        :191
 //   hit <=> |tau - t| <= 1e-12 + 1e-5 |t|   (torch.isclose with its default rtol)                :212,225
 //   the jump acts on the pre-step state unless exact_jumps                                       :214-217
 //   second Brownian driver of 'indep' models = ONE scalar normal shared by all components        :198-201
@@ -209,7 +209,7 @@ struct LazyJumps {
 // ------------------------------------------------------------------------------------------------------------
 struct JumpState {
   float x[kMaxDim];
-  float t, h;
+  float t;
   int k;
   bool need_pop;
 };
@@ -232,8 +232,9 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
   src.begin_iter(s, keys, st.k);
   src.advance(s, keys, st.need_pop);
   const float tau = src.tau;
-  st.h = fminf(st.h, fmaxf(s.T - st.t, 0.0f));
-  const float dt = fmaxf(fminf(st.h, tau - st.t), 0.0f);
+  // h = min(h, max(T - t, 0)) (:190) only ever equals min(h0, max(T - t, 0)) because t never decreases, and fp32
+  // subtraction of the same t is monotone: dt = min(h, tau - t) = min(h0, min(tau, T) - t), clamped at 0 (:191-193)
+  const float dt = fmaxf(fminf(s.h0, fminf(tau, s.T) - st.t), 0.0f);
   const float sq = fast_sqrt(dt);
   float z1[kMaxDim], w1[kMaxDim], w2[kMaxDim], xo[kMaxDim];
 #pragma unroll
@@ -328,7 +329,6 @@ __global__ void __launch_bounds__(256, STORE ? SDEMC_JUMP_STORE_MINB : SDEMC_JUM
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) st.x[d] = d < DIM ? s.x0[d] : 0.0f;
     st.t = 0.0f;
-    st.h = s.h0;
     st.k = 0;
     st.need_pop = true;
     Src src;

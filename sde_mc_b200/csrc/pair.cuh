@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const De
     float xf[kMaxDim], xc[kMaxDim], xof[kMaxDim], xoc[kMaxDim];
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) xf[d] = xc[d] = xof[d] = xoc[d] = d < DIM ? s.x0[d] : 0.0f;
-    float tf = 0.0f, tc = 0.0f, hf = hf0, hc = hc0;
+    float tf = 0.0f, tc = 0.0f;
     int k = 0;
     bool need_pop = true;
     typename std::conditional<INJECT, InjectJumps<MARKS>, InlineJumps<MARKS>>::type src;
@@ -69,8 +69,7 @@ __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const De
           for (int d = 0; d < BASE; ++d) zn[d] = inj.z[zi * DIM + d];
           if (M == 2) zn[BASE] = inj.zc[zi];
         }
-        hf = fminf(hf, fmaxf(s.T - tf, 0.0f));
-        const float dt = fmaxf(fminf(hf, tau - tf), 0.0f);
+        const float dt = fmaxf(fminf(hf0, fminf(tau, s.T) - tf), 0.0f);  // stateless mesh, see jump.cuh
         const float sq = fast_sqrt(dt);
         float z1[kMaxDim], w1[kMaxDim], w2[kMaxDim];
 #pragma unroll
@@ -88,8 +87,7 @@ __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const De
           if (M == 2) s2[d] = fmaf(w2[d], sq, s2[d]);
         }
       }
-      hc = fminf(hc, fmaxf(s.T - tc, 0.0f));                     // :282-286
-      const float dtc = fmaxf(fminf(hc, tau - tc), 0.0f);
+      const float dtc = fmaxf(fminf(hc0, fminf(tau, s.T) - tc), 0.0f);   // :282-286
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) xoc[d] = xc[d];
       euler_step<C>(s, xc, dtc, 1.0f, s1, s2);
