@@ -3,7 +3,7 @@
 //   jump-adapted pair : JumpDiffusionSolver.multilevel_solve solvers.py:228-307
 //   uniform-grid pair : DiffusionSolver.multilevel_solve     solvers.py:90-119
 // Work per level is tiny next to the plain MC kernels (C5 totals ~1e9 fine steps), so these kernels favour
-// simplicity: one Philox block group per fine sub-step, inline jump candidates per outer iteration.
+// simplicity: Brownian normals from a six-per-block shift register, inline jump candidates per outer iteration.
 // Deviation from the reference: dt is clamped at 0 where its fp32 run asserts (solvers.py:264), which is what
 // makes the fp32 pair usable at all.
 #pragma once
@@ -11,6 +11,41 @@
 #include "jump.cuh"
 
 namespace sdemc {
+
+// Philox normals of the Brownian stream, consumed NZ at a time in loop order: one block of six normals serves
+// 6 / NZ consecutive sub-steps (a shift register, so no dynamically indexed registers).
+template <int NZ>
+struct NormalStream {
+  static constexpr int PER = NZ <= 3 ? kNormalsPerBlock / NZ : 1;          // draws served by one refill
+  static constexpr int BLOCKS = NZ <= 3 ? 1 : (NZ + kNormalsPerBlock - 1) / kNormalsPerBlock;
+  float buf[BLOCKS * kNormalsPerBlock];
+  uint32_t blk, plo, phi;
+  int left;
+  __device__ __forceinline__ void init(uint32_t plo_, uint32_t phi_) {
+    plo = plo_;
+    phi = phi_;
+    blk = 0;
+    left = 0;
+  }
+  __device__ __forceinline__ void next(const PhiloxKeys& keys, float (&zn)[NZ]) {
+    if (left == 0) {
+#pragma unroll
+      for (int r = 0; r < BLOCKS; ++r) {
+        uint32_t o[4];
+        philox4x32_10(blk++, STREAM_DIFFUSION, plo, phi, keys, o);
+        philox_normals6(o, buf + kNormalsPerBlock * r);
+      }
+      left = PER;
+    }
+#pragma unroll
+    for (int e = 0; e < NZ; ++e) zn[e] = buf[e];
+    if (PER > 1) {
+#pragma unroll
+      for (int j = 0; j + NZ < kNormalsPerBlock; ++j) buf[j] = buf[j + NZ];
+    }
+    --left;
+  }
+};
 
 struct DevPairOut {
   float* terminal;  // (n, 2, dim): fine, coarse terminal states (parity mode) or nullptr
@@ -44,6 +79,8 @@ __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const De
     typename std::conditional<INJECT, InjectJumps<MARKS>, InlineJumps<MARKS>>::type src;
     if constexpr (INJECT) src.init(s, inj, i);
     else src.init(plo, phi);
+    NormalStream<NZ> normals;
+    normals.init(plo, phi);
 
     while (tf < s.T && k < kcap) {                               // :254
       src.begin_iter(s, keys, k);
@@ -54,15 +91,9 @@ __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const De
       for (int d = 0; d < kMaxDim; ++d) s1[d] = s2[d] = 0.0f;
       for (int q = 0; q < factor; ++q) {                         // :259-278
         const int sub = k * factor + q;
-        float zn[BPS * 4];
+        float zn[NZ];
         if constexpr (!INJECT) {
-#pragma unroll
-          for (int r = 0; r < BPS; ++r) {
-            uint32_t o[4];
-            philox4x32_10((uint32_t)(sub * BPS + r), STREAM_DIFFUSION, plo, phi, keys, o);
-            box_muller(o[0], o[1], zn[4 * r + 0], zn[4 * r + 1]);
-            box_muller(o[2], o[3], zn[4 * r + 2], zn[4 * r + 3]);
-          }
+          normals.next(keys, zn);
         } else {
           const uint64_t zi = i * (uint64_t)inj.K * factor + sub;
 #pragma unroll
@@ -138,21 +169,17 @@ __global__ void __launch_bounds__(256) diffusion_pair_kernel(const DevSde s, con
     float xf[kMaxDim], xc[kMaxDim];
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) xf[d] = xc[d] = d < DIM ? s.x0[d] : 0.0f;
+    NormalStream<NZ> normals;
+    normals.init(plo, phi);
     for (int k = 0; k < coarse; ++k) {
       float s1[kMaxDim], s2[kMaxDim];
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) s1[d] = s2[d] = 0.0f;
       for (int q = 0; q < factor; ++q) {
         const int step = k * factor + q;
-        float zn[BPS * 4];
+        float zn[NZ];
         if constexpr (!INJECT) {
-#pragma unroll
-          for (int r = 0; r < BPS; ++r) {
-            uint32_t o[4];
-            philox4x32_10((uint32_t)(step * BPS + r), STREAM_DIFFUSION, plo, phi, keys, o);
-            box_muller(o[0], o[1], zn[4 * r + 0], zn[4 * r + 1]);
-            box_muller(o[2], o[3], zn[4 * r + 2], zn[4 * r + 3]);
-          }
+          normals.next(keys, zn);
         } else {
           const float* zp = inj.z + (i * (uint64_t)fine + step) * (DIM * M);
 #pragma unroll
