@@ -1,0 +1,83 @@
+"""Path-storing mode: the three data paths out of the SM must write identical trajectories.
+  * TMA tiles (padded 128-byte row pitch, uniform-grid kernel)          csrc/diffusion_tma.cuh
+  * 16-byte vector flush (padded pitch, jump kernels / TMA disabled)    csrc/store_tile.cuh
+  * 4-byte scalar flush (dense rows = the reference's contiguous layout, row_align = 1)
+Checked bit for bit on the same seed, for ragged sizes (1 path, 33 paths, a non-multiple of the CTA size) and for
+shapes whose rows are not a multiple of the tile (partial tiles, clipped by the tensor map / scalar tail)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import sm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _solve(solver_factory, bs, row_align):
+    solver = solver_factory()
+    solver.row_align = row_align
+    out = solver.solve(bs=bs)
+    return out
+
+
+@pytest.mark.parametrize("bs", [1, 33, 1000, 4097])
+@pytest.mark.parametrize("steps", [5, 37, 252])
+def test_diffusion_store_paths_identical_across_layouts(bs, steps):
+    def factory():
+        return sm.EulerSolver(sm.Gbm(0.02, 0.3, torch.tensor([1.0]), 1), 3.0, steps, device=DEV, seed=7)
+
+    p_tma, n_tma = _solve(factory, bs, 32)          # padded pitch -> TMA kernel
+    p_dense, n_dense = _solve(factory, bs, 1)       # dense rows   -> scalar flush
+    assert p_tma.shape == (bs, steps + 1, 1) and n_tma.shape == (bs, steps, 1)
+    assert p_dense.is_contiguous() and n_dense.is_contiguous()
+    assert torch.equal(p_tma, p_dense) and torch.equal(n_tma, n_dense)
+    assert torch.isfinite(p_tma).all() and float(p_tma[:, 0].min()) == 1.0
+    os.environ["SDEMC_NO_TMA_STORE"] = "1"          # padded pitch -> 16-byte vector flush of the LSU kernel
+    try:
+        p_vec, n_vec = _solve(factory, bs, 32)
+    finally:
+        del os.environ["SDEMC_NO_TMA_STORE"]
+    assert torch.equal(p_vec, p_dense) and torch.equal(n_vec, n_dense)
+
+
+@pytest.mark.parametrize("dim,corr", [(2, [0.4]), (3, [0.3, -0.2, 0.5]), (4, None)])
+def test_diffusion_store_multidim_identical_across_layouts(dim, corr):
+    def factory():
+        c = sm.get_corr_matrix(corr) if corr else None
+        return sm.EulerSolver(sm.Gbm(0.02, 0.3, torch.ones(dim), dim, c), 3.0, 50, device=DEV, seed=5)
+
+    p_tma, n_tma = _solve(factory, 777, 32)
+    p_dense, n_dense = _solve(factory, 777, 1)
+    assert torch.equal(p_tma, p_dense) and torch.equal(n_tma, n_dense)
+
+
+def test_heston_and_double_gbm_store_identical_across_layouts():
+    def heston():
+        return sm.HestonSolver(sm.Heston(0.02, 2.0, 0.04, 0.2, -0.7, torch.tensor([1.0, 0.04])), 3.0, 64, device=DEV)
+
+    def dgbm():
+        return sm.EulerSolver(sm.DoubleGbm(0.02, 0.2, 0.1, torch.ones(2), 2, sm.get_corr_matrix([0.3])), 3.0, 40, device=DEV)
+
+    for factory in (heston, dgbm):
+        a, an = _solve(factory, 515, 32)
+        b, bn = _solve(factory, 515, 1)
+        assert torch.equal(a, b) and torch.equal(an, bn)
+
+
+@pytest.mark.parametrize("bs", [1, 33, 1000])
+def test_jump_store_identical_across_layouts(bs):
+    def factory():
+        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1)
+        return sm.JumpEulerSolver(sde, 3.0, 100, device=DEV, seed=3)
+
+    pa, (na, ta, la, ka, ja) = _solve(factory, bs, 32)
+    pb, (nb, tb, lb, kb, jb) = _solve(factory, bs, 1)
+    assert ka == kb
+    for x, y in ((pa, pb), (na, nb), (ta, tb), (la, lb), (ja, jb)):
+        assert x.shape == y.shape and torch.equal(x, y)
+    # the trajectories end at T and the time grid is non-decreasing
+    assert float(ta[:, ka, 0].min()) >= 3.0 - 1e-6
+    assert bool((ta[:, 1:ka + 1, 0] >= ta[:, :ka, 0]).all())
