@@ -284,6 +284,8 @@ def main():
     ev0.record(stream)
     mom = None
     for _ in range(args.steps):
+        if storing:
+            mom = None     # a batch of trajectories is dropped before the next one is simulated (as in the e2e leg)
         mom = device_step()
     ev1.record(stream)
     barrier()

@@ -33,6 +33,6 @@ prof gbm diffusion_kernel 1e8
 prof merton jump1d_kernel 5e7
 prof levy2d jump_kernel 5e6
 prof merton_cv cv_kernel 2e6
-prof gbm_store diffusion_kernel 4e6
+prof gbm_store diffusion_store_tma_kernel 4e6
 prof merton_store jump_kernel 2e6
 ls -la $out | tail -30
