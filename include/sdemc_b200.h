@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SDEMC_ABI_VERSION 2
+#define SDEMC_ABI_VERSION 3
 #define SDEMC_MAX_DIM 4
 #define SDEMC_MAX_LEVELS 16
 
@@ -45,7 +45,13 @@ typedef enum {
  *               LogGbm sde.py:210-219, LevySde(ExampleLevy) levy.py:99-129, LevySde(Levy2d) :163-192
  *   HESTON    : sde.py:258-279 with the drift-implicit square-root scheme schemes.py:16-22
  */
-typedef enum { SDEMC_FAMILY_GEOMETRIC = 0, SDEMC_FAMILY_ARITHMETIC = 1, SDEMC_FAMILY_HESTON = 2 } sdemc_family;
+typedef enum {
+  SDEMC_FAMILY_GEOMETRIC = 0, SDEMC_FAMILY_ARITHMETIC = 1, SDEMC_FAMILY_HESTON = 2,
+  /* USER: coefficients given as CUDA expressions by an Sde subclass (the reference's plugin point, the abstract
+   * drift / diffusion / jumps of sde.py:63-152).  Only libraries JIT-built from csrc/user_model.cu.in accept it
+   * (entry points sdemc_user_mc_moments / sdemc_user_solve_paths, same signatures as the two below). */
+  SDEMC_FAMILY_USER = 3
+} sdemc_family;
 
 /* schemes.py:5-22.  MILSTEIN is an extension (absent from the reference, parity unpinned). */
 typedef enum { SDEMC_SCHEME_EULER = 0, SDEMC_SCHEME_HESTON = 1, SDEMC_SCHEME_MILSTEIN = 2 } sdemc_scheme;
@@ -95,6 +101,8 @@ typedef struct {
   float mark_p[12];
   /* Heston {r, kappa, theta, xi} sde.py:258-279 */
   float heston[4];
+  /* USER family: parameters p[0..15] of the coefficient expressions */
+  float user_p[16];
 } sdemc_sde;
 
 /* Option + discounter: options.py:156-176 (transform), :179-321 (payoffs), :324-337 (ConstantShortRate) */

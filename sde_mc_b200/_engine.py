@@ -57,7 +57,7 @@ def run_moments(solver, payoff, discounter, num_trials, index_mode, moments=None
     step-loop + payoff + reduction kernel.  Returns the Moments holder (all-reduced unless reduce=False)."""
     num_trials = int(num_trials)
     dev = solver._compute_device()
-    lib = L.load()
+    lib = solver._engine_lib()
     rank, size = world()
     lo = solver._take_paths(num_trials)           # every rank advances the global path counter identically
     off, cnt = shard(num_trials, rank, size)
@@ -68,7 +68,8 @@ def run_moments(solver, payoff, discounter, num_trials, index_mode, moments=None
         if moments is None:
             moments = Moments(dev)
         rng = L.SdemcRange(int(solver.seed), lo + off, cnt)
-        L.check(lib.sdemc_mc_moments(sde, po, rng, L.ptr(moments.buf), L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+        getattr(lib, 'check', L.check)(lib.sdemc_mc_moments(sde, po, rng, L.ptr(moments.buf), L.ptr(L.workspace(dev)),
+                                                            L.stream_ptr(dev)))
         if reduce:
             moments.all_reduce()
     return moments

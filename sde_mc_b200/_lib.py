@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SDEMC_B200_LIB", os.path.join(_HERE, "libsdemc_b200.s
 MAX_DIM = 4
 
 # enums (sdemc_b200.h)
-FAMILY_GEOMETRIC, FAMILY_ARITHMETIC, FAMILY_HESTON = 0, 1, 2
+FAMILY_GEOMETRIC, FAMILY_ARITHMETIC, FAMILY_HESTON, FAMILY_USER = 0, 1, 2, 3
 SCHEME_EULER, SCHEME_HESTON, SCHEME_MILSTEIN = 0, 1, 2
 MARKS_NONE, MARKS_LOGNORMAL, MARKS_ICDF = 0, 1, 2
 JUMPS_AUTO, JUMPS_QUEUE, JUMPS_INLINE = 0, 1, 2
@@ -31,6 +31,7 @@ class SdemcSde(C.Structure):
         ("T", C.c_float), ("x0", C.c_float * MAX_DIM), ("chol", C.c_float * (MAX_DIM * MAX_DIM)),
         ("a", C.c_float * MAX_DIM), ("b1", C.c_float * MAX_DIM), ("b2", C.c_float * MAX_DIM),
         ("c", C.c_float * MAX_DIM), ("rate", C.c_float), ("mark_p", C.c_float * 12), ("heston", C.c_float * 4),
+        ("user_p", C.c_float * 16),
     ]
 
 
@@ -103,6 +104,13 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+ABI_VERSION = 3
+
+
+def load_abi_version():
+    return ABI_VERSION
 
 
 def check(rc):

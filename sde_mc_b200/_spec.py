@@ -49,6 +49,8 @@ class KernelSpec:
     mark_p: List[float] = field(default_factory=lambda: [0.0] * 12)
     heston: List[float] = field(default_factory=lambda: [0.0] * 4)
     jump_mean: float = 0.0
+    user_p: List[float] = field(default_factory=lambda: [0.0] * 16)   # USER family: parameters p[]
+    user_code: object = None   # USER family: dict(drift=[...], diffusion=[...], jump=[...]) of CUDA expressions
 
 
 def cholesky_rows(corr_matrix, dim):
@@ -84,6 +86,8 @@ def sde_struct(spec, T, num_steps, max_jumps=0, exact_jumps=False, jump_strategy
         s.mark_p[i] = spec.mark_p[i]
     for i in range(4):
         s.heston[i] = spec.heston[i]
+    for i in range(16):
+        s.user_p[i] = spec.user_p[i]
     return s
 
 
@@ -100,6 +104,14 @@ def payoff_struct(payoff, discount_factor, index_mode):
     p.aux = float(aux)
     p.df = float(discount_factor)
     return p
+
+
+def engine_lib(spec):
+    """the library whose entry points serve this model: the stock engine, or the JIT-built one of a user model"""
+    if spec.family == L.FAMILY_USER:
+        from . import _jit
+        return _jit.library_for(spec)
+    return L.load()
 
 
 def spec_of(sde):

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256, STORE ? SDEMC_DIFF_STORE_MINB : (INJECT ?
   constexpr int SPB = steps_per_group(NZ);      // steps served by one group of Philox blocks (6 normals per block)
   constexpr int BPS = blocks_per_group(NZ);     // Philox blocks per group
   constexpr int NBUF = BPS * kNormalsPerBlock;
-  constexpr bool FAST1D = DIM == 1 && M == 1 && !HESTON && !INJECT && !STORE;
+  constexpr bool FAST1D = DIM == 1 && M == 1 && !HESTON && !INJECT && !STORE && C::FAMILY != SDEMC_FAMILY_USER;
   const int S = s.num_steps;
 
   extern __shared__ float diff_store_smem[];  // STORE: two staging tiles per warp (paths, increments)
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256, STORE ? SDEMC_DIFF_STORE_MINB : (INJECT ?
       for (int d = 0; d < DIM; ++d) wpaths.append(x[d]);
     }
 
+    float t_user = 0.0f;  // fp32 clock of the uniform grid (t += h, solvers.py:83-87); only user coefficients read it
     int b_first = 0;
     if (FAST1D && !s.milstein) {
       // 1-D single-driver moments path (GBM / log-GBM): sigma sqrt(h) is folded into the Box-Muller radius and
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(256, STORE ? SDEMC_DIFF_STORE_MINB : (INJECT ?
           correlate<C>(s, z1, w1);
           if (M == 2) correlate<C>(s, z2, w2);  // DiffusionSolver: every driver is a correlated dim-vector (:79-81)
           if (HESTON) heston_step_uniform(s, x, w1);
-          else euler_step_uniform<C>(s, x, w1, w2);
+          else euler_step_uniform<C>(s, x, w1, w2, t_user);
+          if (C::FAMILY == SDEMC_FAMILY_USER) t_user += s.h0;
           if (STORE) {
 #pragma unroll
             for (int d = 0; d < DIM; ++d) wpaths.stage(sp * DIM + d, x[d]);

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kTmaStoreBlock)
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) x[d] = d < DIM ? s.x0[d] : 0.0f;
     float carry[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // CP pending path elements
+    float t_user = 0.0f;                          // fp32 clock of the grid, read by user coefficients only
     if (DIM == 4) wp.put4(x[0], x[1], x[2], x[3], issued);
 #pragma unroll
     for (int d = 0; d < CP; ++d) carry[d] = x[d];
@@ -193,7 +194,8 @@ __global__ void __launch_bounds__(kTmaStoreBlock)
           if (M == 2) correlate<C>(s, z2, w2);  // DiffusionSolver: every driver is a correlated dim-vector (:79-81)
           if (step < S) {                       // steps past the grid only produce columns the tensor map clips
             if (HESTON) heston_step_uniform(s, x, w1);
-            else euler_step_uniform<C>(s, x, w1, w2);
+            else euler_step_uniform<C>(s, x, w1, w2, t_user);
+            if (C::FAMILY == SDEMC_FAMILY_USER) t_user += s.h0;
           }
 #pragma unroll
           for (int d = 0; d < DIM; ++d) pb[CP + ls * DIM + d] = x[d];

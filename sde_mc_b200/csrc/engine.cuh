@@ -36,6 +36,8 @@ struct DevSde {
       ic_malpha_cp, ic_lda, ic_x3_off, ic_eps_ma, ic_mulda_cp, ic_tol;
   // heston
   float hes_r, hes_kappa, hes_xi, hes_kth, hes_halfxi2;
+  // user-defined coefficient expressions (SDEMC_FAMILY_USER): their parameters
+  float user_p[16];
 };
 
 struct DevPayoff {
@@ -80,6 +82,18 @@ struct Cfg {
 // block; larger NZ -> ceil(NZ/6) blocks per step (slots beyond NZ unused).
 constexpr int steps_per_group(int nz) { return nz <= 3 ? kNormalsPerBlock / nz : 1; }
 constexpr int blocks_per_group(int nz) { return nz <= 3 ? 1 : (nz + kNormalsPerBlock - 1) / kNormalsPerBlock; }
+
+// ------------------------------------------------------------------------------------------------------------
+// user-defined coefficients (SDEMC_FAMILY_USER): a(t, x)_i, b(t, x)_i ('diag' noise) and c(t, x_base, J)_i, the
+// abstract methods of the reference's Sde base class (sde.py:63-152).  A JIT translation unit (user_model.cu.in)
+// defines them from the expressions of an Sde subclass BEFORE including this header; the stock library never
+// instantiates the USER family, the stubs only keep the templates well-formed.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef SDEMC_USER_MODEL
+__device__ __forceinline__ float sdemc_user_drift(int, float, const float*, const float*) { return 0.0f; }
+__device__ __forceinline__ float sdemc_user_diffusion(int, float, const float*, const float*) { return 0.0f; }
+__device__ __forceinline__ float sdemc_user_jump(int, float, const float*, float, const float*) { return 0.0f; }
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // marks
@@ -134,7 +148,16 @@ __device__ __forceinline__ void correlate(const DevSde& s, const float (&z)[kMax
 //   geometric  x (1 + a dt + b1 sq w1 + b2 sq w2)      arithmetic  x + a dt + b1 sq w1 + b2 sq w2
 template <class C>
 __device__ __forceinline__ void euler_step(const DevSde& s, float (&x)[kMaxDim], float dt, float sq,
-                                           const float (&w1)[kMaxDim], const float (&w2)[kMaxDim]) {
+                                           const float (&w1)[kMaxDim], const float (&w2)[kMaxDim], float t = 0.0f) {
+  if (C::FAMILY == SDEMC_FAMILY_USER) {  // x + a(t, x) dt + b(t, x) dW, coefficients at the pre-step state
+    float xin[kMaxDim];
+#pragma unroll
+    for (int i = 0; i < kMaxDim; ++i) xin[i] = x[i];
+#pragma unroll
+    for (int i = 0; i < C::BASE; ++i)
+      x[i] = xin[i] + sdemc_user_drift(i, t, xin, s.user_p) * dt + sdemc_user_diffusion(i, t, xin, s.user_p) * (sq * w1[i]);
+    return;
+  }
   const float x_first = x[0];
 #pragma unroll
   for (int i = 0; i < C::BASE; ++i) {
@@ -159,7 +182,11 @@ __device__ __forceinline__ void euler_step(const DevSde& s, float (&x)[kMaxDim],
 // same, on the uniform grid of DiffusionSolver (h, sqrt(h) folded into per-launch constants ah = a h, b*s = b sqrt(h))
 template <class C>
 __device__ __forceinline__ void euler_step_uniform(const DevSde& s, float (&x)[kMaxDim], const float (&w1)[kMaxDim],
-                                                   const float (&w2)[kMaxDim]) {
+                                                   const float (&w2)[kMaxDim], float t = 0.0f) {
+  if (C::FAMILY == SDEMC_FAMILY_USER) {
+    euler_step<C>(s, x, s.h0, s.sqrt_h0, w1, w2, t);
+    return;
+  }
   const float x_first = x[0];
 #pragma unroll
   for (int i = 0; i < C::BASE; ++i) {
@@ -190,10 +217,12 @@ __device__ __forceinline__ void heston_step_uniform(const DevSde& s, float (&x)[
 
 // sde.jumps(t, x_base, J): geometric c x J (sde.py:374-375, levy.py:154-155), arithmetic c J (levy.py:120-121)
 template <class C>
-__device__ __forceinline__ void add_jump(const DevSde& s, float (&x)[kMaxDim], const float (&xb)[kMaxDim], float J) {
+__device__ __forceinline__ void add_jump(const DevSde& s, float (&x)[kMaxDim], const float (&xb)[kMaxDim], float J,
+                                         float t = 0.0f) {
 #pragma unroll
   for (int i = 0; i < C::BASE; ++i) {
-    if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) x[i] = fmaf(s.c[i] * xb[i], J, x[i]);
+    if (C::FAMILY == SDEMC_FAMILY_USER) x[i] += J != 0.0f ? sdemc_user_jump(i, t, xb, J, s.user_p) : 0.0f;
+    else if (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) x[i] = fmaf(s.c[i] * xb[i], J, x[i]);
     else x[i] = fmaf(s.c[i], J, x[i]);
   }
 }

@@ -83,6 +83,7 @@ inline DevSde to_dev(const sdemc_sde& s, int num_steps) {
     d.ic_mulda_cp = (float)(mu * lda / cp);
     d.ic_tol = (float)(5.960464477539063e-08 / 3.0);
   }
+  for (int i = 0; i < 16; ++i) d.user_p[i] = s.user_p[i];
   d.hes_r = s.heston[0];
   d.hes_kappa = s.heston[1];
   d.hes_xi = s.heston[3];

@@ -244,7 +244,7 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
   for (int i = 0; i < BASE; ++i) w2[i] = M == 2 ? zn[BASE] : 0.0f;
 #pragma unroll
   for (int i = 0; i < kMaxDim; ++i) xo[i] = st.x[i];
-  euler_step<C>(s, st.x, dt, sq, w1, w2);
+  euler_step<C>(s, st.x, dt, sq, w1, w2, st.t);  // user coefficients see t before the step (:204)
   st.t += dt;
   const bool hit = fabsf(tau - st.t) <= fmaf(fabsf(st.t), 1e-5f, 1e-12f);
   // branch-free: a zero mark leaves the state untouched (x + c x_base * 0)
@@ -263,7 +263,7 @@ __device__ __forceinline__ void jump_iteration(const DevSde& s, const PhiloxKeys
 #pragma unroll
     for (int i = 0; i < kMaxDim; ++i) xo[i] = st.x[i];
   }
-  add_jump<C>(s, st.x, xo, Jc);
+  add_jump<C>(s, st.x, xo, Jc, st.t);            // ... and the jump time after it (:214-217)
   st.need_pop = hit;
   ++st.k;
 }

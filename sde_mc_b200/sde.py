@@ -53,6 +53,41 @@ class Sde(ABC):
         """intensity of the Poisson process (tensor)."""
 
     # ---- engine interface -------------------------------------------------------------------------------
+    def kernel_spec(self):
+        """Coefficients for the fused kernels.  Built-in models override this with closed-form coefficient
+        families; a USER-DEFINED subclass (the reference's plugin point: subclass Sde, write drift / diffusion /
+        jumps) gets its own JIT-built kernels by also defining
+
+            def kernel_code(self):
+                return dict(drift=[...], diffusion=[...], jump=[...] or None, params=[...])
+
+        with one CUDA float expression per component in terms of i, t, x[], p[] (and J for the jump coefficient),
+        mirroring its Python tensor methods.  'diag' noise only; jump marks must be the log-normal ones of
+        LogNormalJumpsSde.  See sde_mc_b200/_jit.py and csrc/user_model.cu.in."""
+        code_fn = getattr(self, "kernel_code", None)
+        if code_fn is None:
+            raise L.SdemcError("%s does not publish kernel coefficients: built-in SDE classes do, user-defined ones "
+                               "must define kernel_code() (no CPU fallback)" % type(self).__name__)
+        if self.diffusion_struct != 'diag' or self.brown_dim != self.dim:
+            raise L.SdemcError("user-defined SDEs run on the fused kernels with the 'diag' diffusion structure only")
+        code = dict(code_fn())
+        params = [float(v) for v in code.pop("params", [])]
+        if len(params) > 16:
+            raise L.SdemcError("at most 16 parameters p[] per user-defined SDE")
+        rate = self.jump_rate()
+        has_jumps = bool(torch.as_tensor(rate).any())
+        spec = self._base_spec(L.FAMILY_USER, marks=L.MARKS_LOGNORMAL if has_jumps else L.MARKS_NONE)
+        if has_jumps:
+            if not (hasattr(self, "alpha") and hasattr(self, "gamma")) or code.get("jump") is None:
+                raise L.SdemcError("user-defined jump SDEs need log-normal marks (alpha, gamma as in "
+                                   "LogNormalJumpsSde) and a 'jump' expression in kernel_code()")
+            spec.rate = float(torch.as_tensor(rate).double().sum())
+            spec.mark_p[0], spec.mark_p[1] = float(self.alpha), float(self.gamma)
+            spec.jump_mean = float(self.jump_mean())
+        spec.user_p = params + [0.0] * (16 - len(params))
+        spec.user_code = dict(drift=code["drift"], diffusion=code["diffusion"], jump=code.get("jump"))
+        return spec
+
     def _base_spec(self, family, m=1, marks=L.MARKS_NONE):
         spec = KernelSpec(family=family, dim=self.dim, m=m, marks=marks)
         spec.x0 = _vec(self.init_value, self.dim, 'init_value')

@@ -94,6 +94,10 @@ class SdeSolver(ABC):
         return _spec.sde_struct(spec, self.time_interval, self.num_steps if num_steps is None else num_steps,
                                 self._max_jumps(), self._exact_jumps(), self.jump_strategy)
 
+    def _engine_lib(self):
+        """the library serving this solver's model: the stock engine or the JIT-built one of a user-defined SDE"""
+        return _spec.engine_lib(_spec.spec_of(self.sde))
+
     def _to_user_device(self, t):
         return t if t is None or torch.device(self.device) == t.device else t.to(self.device)
 
@@ -133,7 +137,7 @@ class DiffusionSolver(SdeSolver):
         want_payoff: optional (payoff_struct) to also get per-path discounted payoffs as a third return value."""
         bs = int(bs)
         dev = self._compute_device()
-        lib = L.load()
+        lib = self._engine_lib()
         S, d = int(self.num_steps), self.sde.dim
         m = self.sde.brown_dim // self.sde.dim
         sde = self._sde_struct()
@@ -150,7 +154,8 @@ class DiffusionSolver(SdeSolver):
                 keep.append(z)
                 inj = L.SdemcInject(L.ptr(z), None, None, None, S)
             rng = L.SdemcRange(int(self.seed), self._take_paths(bs), bs)
-            L.check(lib.sdemc_solve_paths(sde, want_payoff, rng, inj, out, L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+            getattr(lib, 'check', L.check)(lib.sdemc_solve_paths(sde, want_payoff, rng, inj, out, L.ptr(L.workspace(dev)),
+                                                                  L.stream_ptr(dev)))
         paths, normals = self._to_user_device(paths), self._to_user_device(normals)
         if want_payoff is not None:
             return paths, normals, self._to_user_device(payoffs)
@@ -219,7 +224,7 @@ class JumpDiffusionSolver(SdeSolver):
         inject: optional dict(z=(bs, K, dim), zc=(bs, K) [indep only], jump_times=(bs, max_jumps), marks=(bs, K))."""
         bs = int(bs)
         dev = self._compute_device()
-        lib = L.load()
+        lib = self._engine_lib()
         d = self.sde.dim
         m = self.sde.brown_dim // d
         sde = self._sde_struct()
@@ -250,7 +255,8 @@ class JumpDiffusionSolver(SdeSolver):
             out = L.SdemcPathsOut(L.ptr(paths), L.ptr(left), L.ptr(times), L.ptr(jumps), L.ptr(normals),
                                   L.ptr(payoffs), L.ptr(iters), L.ptr(total), p_state, p_times, p_norm)
             rng = L.SdemcRange(int(self.seed), self._take_paths(bs), bs)
-            L.check(lib.sdemc_solve_paths(sde, want_payoff, rng, inj, out, L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+            getattr(lib, 'check', L.check)(lib.sdemc_solve_paths(sde, want_payoff, rng, inj, out, L.ptr(L.workspace(dev)),
+                                                                  L.stream_ptr(dev)))
             total_steps = int(total.item())
         self.last_iters = iters
         u = self._to_user_device

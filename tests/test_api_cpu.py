@@ -211,7 +211,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sdemc_version() == 2
+    assert lib.sdemc_version() == 3
     assert lib.sdemc_workspace_bytes() >= 64 + 8 * 8
     assert b"bad argument" in lib.sdemc_strerror(-1) and lib.sdemc_strerror(0) == b"ok"
 
