@@ -64,6 +64,8 @@ def mc_simple(num_trials, sde_solver, payoff, discounter=None, bs=None, return_n
         discounter = ConstantShortRate(r=0.0)
     num_trials = int(num_trials)
     start = time.time()
+    if getattr(payoff, "kernel_spec", None) is None:
+        return _mc_simple_python_payoff(num_trials, sde_solver, payoff, discounter, bs, payoff_time, start)
     if not bs:
         po = _spec.payoff_struct(payoff, float(discounter(sde_solver.time_interval)), _index_mode(payoff_time))
         out, normals, payoffs = sde_solver.solve(bs=num_trials, return_normals=return_normals, want_payoff=po)
@@ -73,6 +75,42 @@ def mc_simple(num_trials, sde_solver, payoff, discounter=None, bs=None, return_n
         return MCStatistics(mean, stderr, time.time() - start, num_trials, out, payoffs, normals)
     mom = E.run_moments(sde_solver, payoff, discounter, num_trials, _index_mode(payoff_time)).read()
     mean, stderr = E.mean_and_stderr(mom['sum'], mom['sumsq'], num_trials)
+    return MCStatistics(mean, stderr, time.time() - start, num_trials)
+
+
+def _mc_simple_python_payoff(num_trials, sde_solver, payoff, discounter, bs, payoff_time, start):
+    """mc_simple for a USER-DEFINED Option subclass (any callable on (bs, dim) tensors, options.py:156-176): the fused
+    kernels cannot evaluate Python code, so trajectories come from the path-storing kernel in batches and the payoff
+    is applied with PyTorch on the GPU, exactly as the reference does (mc.py:84-93); sums are accumulated in fp64."""
+    df = discounter(sde_solver.time_interval)
+    jumps = bool(sde_solver.has_jumps)
+
+    def batch(n):
+        if jumps:
+            out, aux = sde_solver.solve(bs=n, low_storage=bool(bs))
+            idx = aux[3] if (payoff_time == 'adapted' and aux[3] is not None) else sde_solver.num_steps
+            if bs:   # low storage: only `paths` exists; its last column is the adapted index
+                idx = out.shape[1] - 1 if payoff_time == 'adapted' else sde_solver.num_steps
+        else:
+            out, aux = sde_solver.solve(bs=n)
+            idx = sde_solver.num_steps
+        return out, aux, payoff(out[:, idx]) * df
+
+    if not bs:
+        out, aux, payoffs = batch(num_trials)
+        mean, stderr = payoffs.mean(), payoffs.std() / np.sqrt(num_trials)
+        _sync(sde_solver)
+        return MCStatistics(mean, stderr, time.time() - start, num_trials, out, payoffs, aux)
+    total = total_sq = 0.0
+    remaining = num_trials
+    while remaining > 0:
+        n = int(min(bs, remaining))
+        remaining -= n
+        _, _, payoffs = batch(n)
+        p64 = payoffs.double()
+        total = total + p64.sum()
+        total_sq = total_sq + (p64 * p64).sum()
+    mean, stderr = E.mean_and_stderr(float(total), float(total_sq), num_trials)
     return MCStatistics(mean, stderr, time.time() - start, num_trials)
 
 

@@ -154,3 +154,28 @@ def test_user_sde_unsupported_paths_fail_loudly():
         solver.solve(bs=16, inject=dict(z=np.zeros((16, 16, 1, 1), np.float32)))
     with pytest.raises(sm._lib.SdemcError):
         sm.mc_multilevel([1000, 1000], [4, 8], solver, sm.EuroCall(0.0), sm.ConstantShortRate(0.0))
+
+
+def test_user_defined_option_runs_on_stored_paths():
+    """a user Option subclass without kernel coefficients: trajectories from the storing kernel, payoff in PyTorch on
+    the GPU (the reference's own evaluation, mc.py:84-93) -- one-shot and batched, diffusion and jump solvers"""
+
+    class PowerCall(sm.Option):
+        def __init__(self, strike, power):
+            super().__init__(log=False)
+            self.strike, self.power = strike, power
+
+        def payoff(self, x):
+            return torch.clamp(x[:, 0] ** self.power - self.strike, min=0)
+
+    gbm = sm.Gbm(0.02, 0.3, torch.tensor([1.0]), 1)
+    csr = sm.ConstantShortRate(0.02)
+    one = sm.mc_simple(200000, sm.EulerSolver(gbm, 3.0, 32, device=DEV, seed=3), PowerCall(1.0, 1.0), csr)
+    ref = sm.mc_simple(200000, sm.EulerSolver(gbm, 3.0, 32, device=DEV, seed=3), sm.EuroCall(1.0), csr)
+    assert one.payoffs.shape == (200000,) and abs(one.sample_mean - ref.sample_mean) < 1e-6   # power 1 == EuroCall
+    big = sm.mc_simple(4 * 10 ** 6, sm.EulerSolver(gbm, 3.0, 32, device=DEV, seed=3), PowerCall(1.0, 1.0), csr, bs=10 ** 6)
+    assert abs(big.sample_mean - sm.bs_call(1, 1, 3, 0.02, 0.3)) < 4 * big.sample_std + 1e-3
+    merton = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1)
+    jm = sm.mc_simple(2 * 10 ** 6, sm.JumpEulerSolver(merton, 3.0, 50, device=DEV), PowerCall(1.0, 1.0), csr, bs=5 * 10 ** 5,
+                      payoff_time='adapted')
+    assert abs(jm.sample_mean - sm.merton_call(1, 1, 3, 0.02, 0.2, -0.05, 0.3, 1)) < 4 * jm.sample_std + 1e-3
