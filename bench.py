@@ -52,6 +52,11 @@ WORKLOADS.update({
 MLMC_LEVELS = [1, 2, 4, 8, 16, 32, 64, 128]
 MLMC_EPS = 1e-4
 OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0, "mlmc": 40.0})
+# dram__bytes_read.sum + dram__bytes_write.sum of the workload's kernel, per launch, from the `ncu --set full` captures
+# in profiles/r01_ncu_<workload>.summary.txt (moments kernels touch HBM only for code, parameters and the per-CTA
+# partials; the storing kernels write their trajectories once: 1.006x / 1.067x the algorithmic bytes)
+NCU_DRAM_BYTES_PER_LAUNCH = {"gbm": 351488.0, "merton": 29696.0, "levy2d": 68096.0, "merton_cv": 315648.0,
+                             "gbm_store": 8.127e9 + 1.27e8, "merton_store": 5.394306e9 + 3.16317e8, "mlmc": None}
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 
 
@@ -365,7 +370,7 @@ def main():
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak, "unit": "Tlaneop/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                          "ops_per_path_step": OPS_PER_PATH_STEP[args.workload],
                          "peak_def": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock sampled during the run)"
                                      % (sm_count, mhz),
@@ -383,7 +388,7 @@ def main():
                 pass
             hpeak = peaks.get("hbm_gbs", 6650.0)
             out["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hpeak, "unit": "GB/s", "frac": gbs / hpeak,
-                               "traffic": None, "bytes_per_step": store_bytes[0],
+                               "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "bytes_per_step": store_bytes[0],
                                "peak_def": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6.65 TB/s"}
             out["e2e"]["call"] = "solver.solve(bs=paths)  (trajectories stay on the device, as in the reference)"
             out["e2e"]["d2h_bytes_per_step"] = 0
@@ -414,7 +419,7 @@ def main():
                 pass
             tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
             out["roofline_tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
-                                      "frac": tf / tpeak, "traffic": None,
+                                      "frac": tf / tpeak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
                                       "flop_per_path_iteration": CV_TENSOR_FLOP_PER_ITER,
                                       "peak_def": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF"}
         if world == 1 and not args.no_cpu_baseline:
