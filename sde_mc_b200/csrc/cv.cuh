@@ -253,20 +253,35 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
     // ================================ MMA issuer (one thread of warp 8) ========================================
     if (tid == kCvWorkerWarps * 32) {
       uint32_t ph_full[kCvTiles] = {0, 0};
-      auto issue = [&](int tl, int r) {
-        const uint32_t accum = tmem + (uint32_t)tl * 128u;
-        const uint32_t af = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes), ag = af + kCvABytes;
+      // Descriptors are affine in the k-step (the start-address field counts 16-byte units and never carries out of
+      // its 14 bits for addresses below 256 KB), so the issue loop is one 64-bit add per operand and MMA: the
+      // single issuing thread sits on every tile's critical path.
+      uint64_t adesc[kCvTiles][2], bdesc[4][2];
+#pragma unroll
+      for (int tl = 0; tl < kCvTiles; ++tl) {
+        const uint32_t af = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes);
+        adesc[tl][0] = umma_desc(af, 128 * 16, 128);
+        adesc[tl][1] = umma_desc(af + kCvABytes, 128 * 16, 128);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t brows = r == 3 ? kCvHeadN : 64;
         const uint32_t wf = sbase + (r == 0 ? kCvOffW1F : r == 1 ? kCvOffW2F : r == 2 ? kCvOffW3F : kCvOffW4F);
         const uint32_t wg = sbase + (r == 0 ? kCvOffW1G : r == 1 ? kCvOffW2G : r == 2 ? kCvOffW3G : kCvOffW4G);
+        bdesc[r][0] = umma_desc(wf, brows * 16, 128);
+        bdesc[r][1] = umma_desc(wg, brows * 16, 128);
+      }
+      auto issue = [&](int tl, int r) {
+        const uint32_t accum = tmem + (uint32_t)tl * 128u;
         const int ksteps = r == 0 ? 1 : 4;
-        const uint32_t brows = r == 3 ? kCvHeadN : 64;
         const uint32_t idesc = r == 3 ? cv_idesc(kCvHeadN) : cv_idesc(64);
+        const uint64_t a_step = (2u * (128 * 16)) >> 4;                                   // two 16-byte chunks of A
+        const uint64_t b_step = (2u * ((r == 3 ? kCvHeadN : 64) * 16)) >> 4;
+        uint64_t daf = adesc[tl][0], dag = adesc[tl][1], dbf = bdesc[r][0], dbg = bdesc[r][1];
         for (int ks = 0; ks < ksteps; ++ks) {
-          umma_bf16(accum, umma_desc(af + ks * 2 * (128 * 16), 128 * 16, 128),
-                    umma_desc(wf + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
-          if (JUMPS)
-            umma_bf16(accum + 64, umma_desc(ag + ks * 2 * (128 * 16), 128 * 16, 128),
-                      umma_desc(wg + ks * 2 * (brows * 16), brows * 16, 128), idesc, ks > 0);
+          umma_bf16(accum, daf, dbf, idesc, ks > 0);
+          if (JUMPS) umma_bf16(accum + 64, dag, dbg, idesc, ks > 0);
+          daf += a_step; dag += a_step; dbf += b_step; dbg += b_step;
         }
         umma_commit(bar_done + 8 * tl);
       };
