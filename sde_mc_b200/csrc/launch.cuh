@@ -14,6 +14,7 @@ struct LaunchArgs {
   bool use_inject;
   bool store;
   int qdepth;          // jump queue depth (multiple of 4), 0 => inline jump strategy
+  bool flat = false;   // short paths: persistent-lane kernel (set by launch_jump)
   double* d_moments;
   void* d_ws;
   cudaStream_t stream;

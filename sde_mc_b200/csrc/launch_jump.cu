@@ -1,7 +1,11 @@
 // launch_jump.cu -- instantiation + dispatch of the jump-adapted kernels (jump.cuh)
 #include <type_traits>
 
+#include <cmath>
+#include <cstdlib>
+
 #include "jump1d.cuh"
+#include "jump_flat.cuh"
 #include "launch.cuh"
 
 namespace sdemc {
@@ -39,6 +43,27 @@ int run_1d(const LaunchArgs& a) {
   return SDEMC_OK;
 }
 
+// moments-only kernel for short paths with inline jumps: lanes are persistent workers (jump_flat.cuh)
+template <class C>
+int run_flat(const LaunchArgs& a) {
+  auto kernel = jump_flat_kernel<C>;
+  int grid = 0;
+  int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
+  if (rc != SDEMC_OK) return rc;
+  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.d_moments, a.d_ws);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+
+// A warp of jump_kernel runs until its slowest lane is done: E[max of 32 Poisson(rate T)] exceeds the mean by about
+// 2.1 sqrt(rate T) iterations.  When that is more than a fifth of a path's num_steps + rate T iterations the
+// persistent-lane kernel wins (MLMC level 0: 2.1 * 1.7 / 4).  SDEMC_JUMP_FLAT=0/1 overrides (benchmarks).
+bool want_flat(const sdemc_sde& s) {
+  if (const char* e = getenv("SDEMC_JUMP_FLAT")) return atoi(e) != 0;
+  const double lam_T = (double)s.rate * (double)s.T;
+  return 2.1 * std::sqrt(lam_T) > 0.2 * ((double)s.num_steps + lam_T);
+}
+
 template <class C>
 int by_mode(const LaunchArgs& a) {
   if constexpr (C::DIM == 1 && C::M == 1 && !C::ASIAN) {
@@ -46,6 +71,7 @@ int by_mode(const LaunchArgs& a) {
       return a.sde.exact_jumps ? run_1d<C, true>(a) : run_1d<C, false>(a);
   }
   if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;
+  if (a.flat && !a.store && a.qdepth == 0) return run_flat<C>(a);
   if (a.qdepth > 0) return a.store ? run<C, JSRC_QUEUE, true>(a) : run<C, JSRC_QUEUE, false>(a);
   return a.store ? run<C, JSRC_INLINE, true>(a) : run<C, JSRC_INLINE, false>(a);
 }
@@ -63,7 +89,9 @@ int by_dim(const sdemc_sde& s, const LaunchArgs& a) {
 
 }  // namespace
 
-int launch_jump(const sdemc_sde& s, const LaunchArgs& a) {
+int launch_jump(const sdemc_sde& s, const LaunchArgs& a_in) {
+  LaunchArgs a = a_in;
+  a.flat = want_flat(s);
   if (a.qdepth < 0 || (a.qdepth & 3) || a.qdepth > 64) return SDEMC_ERR_BAD_ARG;
   if (s.asian) {
     if (s.dim == 2 && s.m == 1 && s.family == SDEMC_FAMILY_GEOMETRIC && s.marks == SDEMC_MARKS_LOGNORMAL)

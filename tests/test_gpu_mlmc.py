@@ -113,3 +113,41 @@ def test_mc_multilevel_works_for_diffusions_too():
     levels = [2, 8, 32, 128]
     st = sm.mc_multilevel([2 * 10 ** 6, 4 * 10 ** 5, 10 ** 5, 3 * 10 ** 4], levels, p.solver, p.payoff, p.discounter)
     assert abs(st.sample_mean - sm.bs_call(1, 1, 3, 0.02, 0.3)) <= 1.96 * st.sample_std + 3e-4
+
+
+@pytest.mark.parametrize("case", ["merton_1step", "merton_3steps_terminal", "levy2d_2steps", "merton2d_exact"])
+def test_short_path_kernel_matches_generic_kernel(case, monkeypatch):
+    """jump_flat.cuh (persistent lanes, chosen for short paths such as MLMC level 0) simulates the SAME paths as the
+    generic jump kernel: identical path count and iteration total, moments equal up to the fp64 summation order."""
+    from sde_mc_b200 import _engine as E
+    from sde_mc_b200 import _lib as L
+    from sde_mc_b200 import _spec
+    if case.startswith("merton_"):
+        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+        payoff = sm.EuroCall(1.0)
+    elif case == "merton2d_exact":
+        sde = sm.Merton(0.02, 0.2, 2, -0.05, 0.3, torch.tensor([1., 1.1]), 2, sm.get_corr_matrix([0.4]))
+        payoff = sm.Rainbow(1.0)
+    else:
+        levy = sm.ExpExampleLevy(1, 1, .5, 2, .02, .3, .2, .05, dim=2)
+        sde = sm.LevySde(levy, torch.tensor([1., 1.]))
+        payoff = sm.Rainbow(1.0)
+    steps = {"merton_1step": 1, "merton_3steps_terminal": 3, "levy2d_2steps": 2, "merton2d_exact": 1}[case]
+    solver = sm.JumpEulerSolver(sde, 3, steps, device=DEV, exact_jumps=case == "merton2d_exact")
+    mode = L.INDEX_TERMINAL if case.endswith("terminal") else L.INDEX_ADAPTED
+    n = 300_001  # ragged: the last warp is partial and lanes run out of paths at different times
+    lib = L.load()
+    res = {}
+    for flat in ("0", "1"):
+        monkeypatch.setenv("SDEMC_JUMP_FLAT", flat)
+        with torch.cuda.device(DEV):
+            mom = E.Moments(torch.device(DEV, 0))
+            po = _spec.payoff_struct(payoff, math.exp(-0.06), mode)
+            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(7, 123, n), L.ptr(mom.buf),
+                                         L.ptr(L.workspace(torch.device(DEV, 0))), L.stream_ptr(torch.device(DEV, 0))))
+            res[flat] = mom.read()
+    a, b = res["0"], res["1"]
+    assert a["n"] == b["n"] == n
+    assert a["iters"] == b["iters"] and a["iters"] > n * steps
+    for key in ("sum", "sumsq"):
+        assert abs(a[key] - b[key]) <= 1e-11 * abs(a[key]), (key, a[key], b[key])
