@@ -4,19 +4,28 @@
 // ~20 B per path-step through HBM) -> apply_adapted_control_variates varred.py:98-131 (two MLP forwards over
 // bs*S rows), resp. the diffusion variant varred.py:75-95.
 //
-// Tensor cores (tcgen05, accumulators in TMEM): a CTA of 256 threads owns TWO tiles of 128 paths; path r of a tile is
-// row r of its activation matrices and lane r of its TMEM accumulators.  Warps 0-3 own (simulate) the paths of tile
-// 0, warps 4-7 those of tile 1; in the epilogues every row is shared by the two warps of its TMEM lane quadrant,
-// 32 accumulator columns each.  Each time step evaluates
+// Tensor cores (tcgen05, accumulators AND the activation operand in TMEM): path r of a tile of 128 paths is lane r of
+// the tile's 128 TMEM columns -- 64 fp32 accumulator columns D shared by both nets, 32 columns A_f and 32 columns
+// A_g holding the nets' current activation vectors as bf16 pairs (column c = units 2c, 2c+1).  Each time step evaluates
 //   Linear(2,H) ReLU Linear(H,H) ReLU Linear(H,H) ReLU Linear(H,1)         (nets.py:39-93, BN-free, H <= 63)
-// for both nets as FOUR rounds of tcgen05.mma per tile (M=128; N=64,K=16 | N=64,K=64 | N=64,K=64 | N=16,K=64; bf16
-// in, fp32 accumulate) whose A operand the threads write themselves into shared memory in the canonical K-major
-// no-swizzle UMMA layout.  The two tiles are software-pipelined against each other: while the tensor core runs
-// round r of one tile, the threads run the epilogue of the other tile (TMEM -> ReLU -> bf16 -> next A operand), so
-// MMA latency, commit/mbarrier latency and the CTA barrier of one tile hide behind SIMT work of the other.
+// for both nets as EIGHT phases per tile, f and g alternating: (layer 1, f) (layer 1, g) (layer 2, f) ... (head, g),
+// each one `tcgen05.mma.cta_group::1.kind::f16 [D], [A_net], b_desc` chain (M=128; N=64,K=16 | N=64,K=64 | N=64,K=64 |
+// N=16,K=64; bf16 in, fp32 accumulate) with the weights (B) in shared memory.  The four worker warps of a tile (one
+// per TMEM lane quadrant) read D with tcgen05.ld, release it, and while the tensor core already runs the OTHER
+// net's phase into D they apply ReLU, pack to bf16 and write the next activation vector back with tcgen05.st.
+// Why the activations live in TMEM: with A in shared memory (rounds of the first version of this kernel) every
+// K=16 MMA pulls 4 KB of A and 2 KB of B through the tensor core's shared-memory port at 128 B/clk -- 48 clk for an
+// instruction whose math takes 32 -- and the epilogues write the same bytes through the LSU: ncu showed
+// l1tex__data_pipe_tc_wavefronts_mem_shared at 65 % and sm__pipe_tc_cycles_active at 79 % with the tensor math only
+// 36 % busy (profiles/r01_ncu_merton_cv.*).  From TMEM the A operand costs no shared-memory bandwidth at all, the
+// generic->async proxy fence of every round disappears, and sharing D between the nets keeps a tile at 128 columns,
+// so four tiles (2 CTAs x 2) are still resident per SM to hide each other's MMA / commit / wake-up latency.
+// Every tile is an independent chain with its own issuer warp; there is no CTA barrier in the step loop.
 // Biases are folded into the contraction: every padded activation vector carries a constant 1 in slot 63
-// (W[n][63] = b[n], W[63][63] = 1).  The inputs (t, x) are split into bf16 hi + lo parts (two K slots each with the
-// same weight) so the nets are evaluated at fp32-accurate inputs; weights and hidden activations are bf16.
+// (W[n][63] = b[n]); for H <= 56 the epilogue writes that constant itself and reads only 56 accumulator columns
+// (TMEM reads are the tightest floor of a step), otherwise W[63][63] = 1 carries it through the MMA.
+// The inputs (t, x) are split into bf16 hi + lo parts (two K slots each with the same weight) so the nets are
+// evaluated at fp32-accurate inputs; weights and hidden activations are bf16.
 // Any adapted f, g gives an unbiased estimator, so the reduced precision only perturbs the variance reduction.
 #pragma once
 #include <cuda_bf16.h>
@@ -33,19 +42,27 @@ struct DevMlp {
   int in_dim, hidden, out_dim;
 };
 
-constexpr int kCvRows = 128;     // paths per tile = rows of the activation matrices = TMEM lanes
-constexpr int kCvWorkerWarps = 8; // warps 0-3 own the paths of tile 0, warps 4-7 those of tile 1; all 8 share the epilogues
-constexpr int kCvThreads = (kCvWorkerWarps + 1) * 32;  // + the MMA issuer warp
+constexpr int kCvRows = 128;      // paths per tile = TMEM lanes
+constexpr int kCvTiles = 2;       // path tiles per CTA, independent chains
+constexpr int kCvWorkerWarps = 4 * kCvTiles;  // warps 4*tl .. 4*tl+3: paths and epilogues of tile tl
+constexpr int kCvIssuerWarps = kCvTiles;      // warp kCvWorkerWarps + tl issues the MMAs of tile tl (one thread)
+constexpr int kCvThreads = (kCvWorkerWarps + kCvIssuerWarps) * 32;
 constexpr int kCvOne = 63;  // index of the constant-one unit in every padded (64-wide) activation vector
 
-// shared-memory carve-up (bytes).  Operand tiles: 16-byte chunk c = k/8 of row r lives at c * (rows*16) + r * 16,
-// i.e. UMMA descriptors with LBO = rows*16 (K direction) and SBO = 128 (next group of 8 rows).
-constexpr int kCvTiles = 2;                 // path tiles per CTA, pipelined against each other
+// TMEM columns of a tile
+constexpr int kCvColD = 0;      // 64 fp32 accumulators (the head uses the first 16)
+constexpr int kCvColAf = 64;    // activation vector of f: 32 columns = 64 bf16
+constexpr int kCvColAg = 96;    // activation vector of g
+constexpr int kCvTileCols = 128;
+constexpr int kCvTmemCols = kCvTileCols * kCvTiles;
+
+// shared-memory carve-up (bytes).  Weight (B operand) tiles in the canonical K-major no-swizzle UMMA layout: 16-byte
+// chunk c = k/8 of row n lives at c * (rows*16) + n * 16, i.e. descriptors with LBO = rows*16 (K direction) and
+// SBO = 128 (next group of 8 rows).
 constexpr int kCvHeadN = 16;                // N of the head MMA (smallest N for M = 128); only column 0 is used
 constexpr int kCvW1Bytes = 64 * 16 * 2;
 constexpr int kCvWBytes = 64 * 64 * 2;
 constexpr int kCvW4Bytes = kCvHeadN * 64 * 2;
-constexpr int kCvABytes = 128 * 64 * 2;
 constexpr int kCvOffW1F = 0;
 constexpr int kCvOffW1G = kCvOffW1F + kCvW1Bytes;
 constexpr int kCvOffW2F = kCvOffW1G + kCvW1Bytes;
@@ -54,12 +71,10 @@ constexpr int kCvOffW2G = kCvOffW3F + kCvWBytes;
 constexpr int kCvOffW3G = kCvOffW2G + kCvWBytes;
 constexpr int kCvOffW4F = kCvOffW3G + kCvWBytes;
 constexpr int kCvOffW4G = kCvOffW4F + kCvW4Bytes;
-constexpr int kCvOffA = kCvOffW4G + kCvW4Bytes;  // per tile: A_f then A_g
-constexpr int kCvOffBar = kCvOffA + kCvTiles * 2 * kCvABytes;
+constexpr int kCvOffBar = kCvOffW4G + kCvW4Bytes;
 constexpr int kCvOffTmem = kCvOffBar + 16 * kCvTiles;  // full[tile] then done[tile]
 constexpr int kCvOffFlags = kCvOffTmem + 8;            // int any_active[tile][parity], int live[tile]
 constexpr int kCvSmemBytes = kCvOffFlags + 4 * 3 * kCvTiles + 8;
-constexpr int kCvTmemCols = 128 * kCvTiles;  // per tile: f accumulators in columns 0-63, g in 64-127
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -74,12 +89,14 @@ constexpr uint32_t cv_idesc(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
-                                          uint32_t accumulate) {
+// D[tmem_d] (+)= A[tmem_a] * B[db]^T : A operand in TMEM (lane = row, 32-bit column c = bf16 pair k = 2c, 2c+1; layout
+// verified by tools/umma_ts_f16_test.cu), B operand in shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate));
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate));
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -100,44 +117,86 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(uint32_t lo_bits, uint32_t 
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
   return r;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
+// tcgen05.ld / tcgen05.st of this warp's 32 lanes x N consecutive 32-bit columns (asynchronous: tmem_wait_ld / _st)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// epilogue of a hidden layer, one half (32 accumulator columns) per thread: ReLU -> bf16 -> chunks 4*half .. 4*half+3
-// of this row of the next A operand.  taddr / a_row_addr already point at the half.
-__device__ __forceinline__ void hidden_epilogue_half(uint32_t taddr, uint32_t a_row_addr) {
-  uint32_t v[32];
-  tmem_ld32(taddr, v);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    sts128(a_row_addr + c * (kCvRows * 16), relu_pack_bf16x2(v[8 * c + 0], v[8 * c + 1]),
-           relu_pack_bf16x2(v[8 * c + 2], v[8 * c + 3]), relu_pack_bf16x2(v[8 * c + 4], v[8 * c + 5]),
-           relu_pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// The accumulator row of a hidden layer, read out of D.  NARROW (H <= 56): only columns 0-55 (32 + 16 + 8).
+template <bool NARROW>
+struct CvAccRow {
+  uint32_t lo[32];
+  uint32_t mid[16];
+  uint32_t hi[NARROW ? 8 : 16];
+  __device__ __forceinline__ void load(uint32_t tacc) {
+    tmem_ld32(tacc, lo);
+    tmem_ld16(tacc + 32, mid);
+    if constexpr (NARROW) tmem_ld8(tacc + 48, hi);
+    else tmem_ld16(tacc + 48, hi);
+    tmem_wait_ld();
   }
-}
-// output of the head MMA: column 0 of this thread's accumulator row
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
-  uint32_t v;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  return __uint_as_float(v);
-}
-// first-layer A row: [t_hi, t_lo, x_hi, x_lo, 1, 0, 0, 0 | 0 x 8]
-__device__ __forceinline__ void write_input_row(uint32_t a_row_addr, float t, float x) {
+  // ReLU -> bf16 pairs -> the 32 columns of the next activation vector; slot 63 = the constant 1 (NARROW: written here,
+  // otherwise computed by the MMA through W[63][63] = 1)
+  __device__ __forceinline__ void store_relu(uint32_t ta) const {
+    uint32_t a[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a[c] = relu_pack_bf16x2(lo[2 * c], lo[2 * c + 1]);
+    tmem_st16(ta, a);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = relu_pack_bf16x2(mid[2 * c], mid[2 * c + 1]);
+    if constexpr (NARROW) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a[8 + c] = relu_pack_bf16x2(hi[2 * c], hi[2 * c + 1]);
+      a[12] = a[13] = a[14] = 0u;
+      a[15] = 0x3f800000u;  // (unit 62 = 0, unit 63 = 1.0bf16)
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[8 + c] = relu_pack_bf16x2(hi[2 * c], hi[2 * c + 1]);
+    }
+    tmem_st16(ta + 16, a);
+  }
+};
+// first-layer activation vector (K = 16 -> 8 columns): [t_hi, t_lo | x_hi, x_lo | 1, 0 | 0 ...]
+__device__ __forceinline__ void write_input_row(uint32_t ta, float t, float x) {
   const __nv_bfloat16 th = __float2bfloat16_rn(t), xh = __float2bfloat16_rn(x);
   const __nv_bfloat16 tl = __float2bfloat16_rn(t - __bfloat162float(th)), xl = __float2bfloat16_rn(x - __bfloat162float(xh));
-  const uint32_t p0 = (uint32_t)__bfloat16_as_ushort(th) | ((uint32_t)__bfloat16_as_ushort(tl) << 16);
-  const uint32_t p1 = (uint32_t)__bfloat16_as_ushort(xh) | ((uint32_t)__bfloat16_as_ushort(xl) << 16);
-  sts128(a_row_addr, p0, p1, 0x00003f80u /* (1.0bf16, 0) */, 0u);
-  sts128(a_row_addr + 128 * 16, 0u, 0u, 0u, 0u);
+  uint32_t a[8];
+  a[0] = (uint32_t)__bfloat16_as_ushort(th) | ((uint32_t)__bfloat16_as_ushort(tl) << 16);
+  a[1] = (uint32_t)__bfloat16_as_ushort(xh) | ((uint32_t)__bfloat16_as_ushort(xl) << 16);
+  a[2] = 0x00003f80u;  // (1.0bf16, 0)
+#pragma unroll
+  for (int c = 3; c < 8; ++c) a[c] = 0u;
+  tmem_st8(ta, a);
 }
 
 // weights -> bf16 canonical operand tiles with folded biases (see header comment)
@@ -195,14 +254,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // 1-D 'diag' SDE (dim == 1, m == 1): Merton-type jump diffusion (JUMPS) or GBM-type diffusion (!JUMPS)
 //
-// Warp roles: warps 0-7 are workers (warps 0-3 own the paths of tile 0, warps 4-7 those of tile 1; in the hidden-layer
-// epilogues every row is shared by the two warps of its TMEM lane quadrant, 32 accumulator columns each); warp 8 is
-// the MMA issuer (one thread).  Hand-off per tile is by two mbarriers, no CTA barrier in the loop:
-//   full[tl]  (256 arrivals)  workers -> issuer : the A operands of the next round are in shared memory
-//   done[tl]  (1 arrival)     issuer  -> workers: tcgen05.commit of that round's MMAs (or a plain arrive when the tile
-//                                                 has no active path left; tile_live[tl] says which)
-// Both sides walk the same (step, round, tile) sequence, so while the issuer and the tensor core work on one tile
-// the workers convert or advance the other.
+// Warp roles: warps 4*tl .. 4*tl+3 are the workers of tile tl (thread = path = TMEM lane; a warp can only access the
+// TMEM lanes of its quadrant, warp % 4); warp kCvWorkerWarps + tl is the MMA issuer of tile tl (one thread).
+// Hand-off per tile is by two mbarriers, no CTA barrier in the loop:
+//   full[tl]  (4 arrivals)    workers -> issuer : D has been read (the next phase may overwrite it) and the
+//                                                 activation vector that phase consumes is in TMEM
+//   done[tl]  (1 arrival)     issuer  -> workers: tcgen05.commit of a phase's MMAs (or a plain arrive when the tile
+//                                                 has no active path left; live[tl] says which)
+// With two nets the phases alternate f, g, f, g ...: a worker arrives on full right after its tcgen05.ld of D and
+// converts / stores the activations of the net just read while the tensor core runs the other net -- the vector the
+// next phase consumes was stored during the PREVIOUS phase, i.e. before this arrival in program order.  With one net
+// (diffusions) the arrival follows the store.
 template <class C, bool JUMPS, bool INJECT>
 __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                         const PhiloxKeys keys, const DevInject inj, const DevMlp f,
@@ -210,23 +272,25 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
   extern __shared__ __align__(1024) uint8_t cv_smem[];
   constexpr int MARKS = C::MARKS;
+  constexpr int NETS = JUMPS ? 2 : 1;
   using Src = typename std::conditional<INJECT, InjectJumps<MARKS>, LazyJumps<MARKS>>::type;
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool worker = warp < kCvWorkerWarps;
   const int quad = warp & 3;        // TMEM lane quadrant this warp may access (lanes 32*quad .. 32*quad+31)
-  const int mine = (warp >> 2) & 1; // tile whose paths this thread owns; also the column half it converts
+  const int mine = worker ? (warp >> 2) : (warp - kCvWorkerWarps);  // the tile this warp works for
   const int row = quad * 32 + (tid & 31);
   const uint32_t sbase = smem_u32(cv_smem);
-  const uint32_t bar_full = sbase + kCvOffBar, bar_done = bar_full + 8 * kCvTiles;
+  const uint32_t bar_full = sbase + kCvOffBar + 8 * mine, bar_done = sbase + kCvOffBar + 8 * kCvTiles + 8 * mine;
   volatile int* flags = reinterpret_cast<volatile int*>(cv_smem + kCvOffFlags);  // [tile][parity] any-active, then live[tile]
+  const bool narrow = f.hidden <= 56 && (!JUMPS || g.hidden <= 56);  // CTA-uniform: 56-column epilogues
 
   load_mlp(f, cv_smem + kCvOffW1F, cv_smem + kCvOffW2F, cv_smem + kCvOffW3F, cv_smem + kCvOffW4F);
   if (JUMPS) load_mlp(g, cv_smem + kCvOffW1G, cv_smem + kCvOffW2G, cv_smem + kCvOffW3G, cv_smem + kCvOffW4G);
   if (tid == 0) {
 #pragma unroll
     for (int tl = 0; tl < kCvTiles; ++tl) {
-      mbar_init(bar_full + 8 * tl, kCvWorkerWarps * 32);
-      mbar_init(bar_done + 8 * tl, 1);
+      mbar_init(sbase + kCvOffBar + 8 * tl, 4);  // one arrival per worker warp
+      mbar_init(sbase + kCvOffBar + 8 * kCvTiles + 8 * tl, 1);
     }
     for (int q = 0; q < 3 * kCvTiles; ++q) flags[q] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;");
@@ -236,12 +300,12 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
                  "n"(kCvTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the weight tiles -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *reinterpret_cast<const uint32_t*>(cv_smem + kCvOffTmem);
-  const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);  // this warp's 32 TMEM lanes
+  const uint32_t tile_cols = tmem + (uint32_t)mine * kCvTileCols;
 
   const int n = s.num_steps;
   const int kcap = JUMPS ? (INJECT ? inj.K : 4 * (n + s.max_jumps) + 64) : n;
@@ -250,19 +314,10 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
   acc.zero();
 
   if (!worker) {
-    // ================================ MMA issuer (one thread of warp 8) ========================================
-    if (tid == kCvWorkerWarps * 32) {
-      uint32_t ph_full[kCvTiles] = {0, 0};
-      // Descriptors are affine in the k-step (the start-address field counts 16-byte units and never carries out of
-      // its 14 bits for addresses below 256 KB), so the issue loop is one 64-bit add per operand and MMA: the
-      // single issuing thread sits on every tile's critical path.
-      uint64_t adesc[kCvTiles][2], bdesc[4][2];
-#pragma unroll
-      for (int tl = 0; tl < kCvTiles; ++tl) {
-        const uint32_t af = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes);
-        adesc[tl][0] = umma_desc(af, 128 * 16, 128);
-        adesc[tl][1] = umma_desc(af + kCvABytes, 128 * 16, 128);
-      }
+    // ========================= MMA issuer of tile `mine` (one thread of warp 8 + mine) ==========================
+    if ((tid & 31) == 0) {
+      uint32_t ph_full = 0;
+      uint64_t bdesc[4][2];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t brows = r == 3 ? kCvHeadN : 64;
@@ -271,53 +326,50 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
         bdesc[r][0] = umma_desc(wf, brows * 16, 128);
         bdesc[r][1] = umma_desc(wg, brows * 16, 128);
       }
-      auto issue = [&](int tl, int r) {
-        const uint32_t accum = tmem + (uint32_t)tl * 128u;
+      // phase (layer r, net): D[dcol ..] = A_net * W_r,net^T.  The B descriptor is affine in the k-step (the
+      // start-address field counts 16-byte units and never carries out of its 14 bits below 256 KB); A advances 8
+      // columns per k-step.
+      auto issue = [&](int r, int net, uint32_t dcol, bool commit) {
         const int ksteps = r == 0 ? 1 : 4;
         const uint32_t idesc = r == 3 ? cv_idesc(kCvHeadN) : cv_idesc(64);
-        const uint64_t a_step = (2u * (128 * 16)) >> 4;                                   // two 16-byte chunks of A
         const uint64_t b_step = (2u * ((r == 3 ? kCvHeadN : 64) * 16)) >> 4;
-        uint64_t daf = adesc[tl][0], dag = adesc[tl][1], dbf = bdesc[r][0], dbg = bdesc[r][1];
+        uint64_t db = bdesc[r][net];
+        uint32_t ta = tile_cols + (net ? kCvColAg : kCvColAf);
         for (int ks = 0; ks < ksteps; ++ks) {
-          umma_bf16(accum, daf, dbf, idesc, ks > 0);
-          if (JUMPS) umma_bf16(accum + 64, dag, dbg, idesc, ks > 0);
-          daf += a_step; dag += a_step; dbf += b_step; dbg += b_step;
+          umma_bf16_ts(tile_cols + kCvColD + dcol, ta, db, idesc, ks > 0);
+          ta += 8;
+          db += b_step;
         }
-        umma_commit(bar_done + 8 * tl);
+        if (commit) umma_commit(bar_done);
       };
-      // round 0 of a step starts only if some path of the tile is still active (flag written by its owners)
-      auto start_step = [&](int tl, int par) -> bool {
-        mbar_wait(bar_full + 8 * tl, ph_full[tl]);
-        ph_full[tl] ^= 1u;
+      auto wait_workers = [&]() {
+        mbar_wait(bar_full, ph_full);
+        ph_full ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool any = flags[tl * 2 + par] != 0;
-        flags[tl * 2 + par] = 0;
-        flags[2 * kCvTiles + tl] = any ? 1 : 0;
+      };
+      // the first phase of a step starts only if some path of the tile is still active (flag written by its owners)
+      auto start_step = [&](int par) -> bool {
+        wait_workers();
+        const bool any = flags[mine * 2 + par] != 0;
+        flags[mine * 2 + par] = 0;
+        flags[2 * kCvTiles + mine] = any ? 1 : 0;
         __threadfence_block();  // flag writes before the arrival (commit or plain) the workers synchronise on
-        if (any) issue(tl, 0);
-        else mbar_arrive(bar_done + 8 * tl);
+        if (any) issue(0, 0, 0, true);
+        else mbar_arrive(bar_done);
         return any;
       };
       for (uint64_t pair = blockIdx.x; pair * kCvTiles < n_tiles; pair += gridDim.x) {
-        bool live[kCvTiles];
+        bool live = start_step(0);
+        for (int k = 0; live; ++k) {
 #pragma unroll
-        for (int tl = 0; tl < kCvTiles; ++tl) live[tl] = start_step(tl, 0);
-        for (int k = 0; live[0] || live[1]; ++k) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-#pragma unroll
-            for (int tl = 0; tl < kCvTiles; ++tl) {
-              if (!live[tl]) continue;
-              if (r < 3) {
-                mbar_wait(bar_full + 8 * tl, ph_full[tl]);
-                ph_full[tl] ^= 1u;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue(tl, r + 1);
-              } else {
-                live[tl] = start_step(tl, (k + 1) & 1);
-              }
-            }
+          for (int ph = 1; ph < 3 * NETS; ++ph) {  // hidden layers, f and g alternating
+            wait_workers();
+            issue(ph / NETS, ph % NETS, 0, true);
           }
+          wait_workers();                            // heads of both nets in one phase: D columns 0-15 and 16-31
+          issue(3, 0, 0, !JUMPS);
+          if (JUMPS) issue(3, 1, kCvHeadN, true);
+          live = start_step((k + 1) & 1);
         }
       }
     }
@@ -333,9 +385,9 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
       Src src;
     };
     Path p;
-    uint32_t ph_done[kCvTiles] = {0, 0};
+    uint32_t ph_done = 0;
 #ifdef SDEMC_CV_PROFILE
-    long long prof_wait = 0, prof_epi = 0, prof_ready = 0, prof_adv = 0, prof_t0 = clock64(), prof_rounds = 0;
+    long long prof_wait = 0, prof_epi = 0, prof_adv = 0, prof_t0 = clock64(), prof_steps = 0;
 #define CVP_BEGIN long long cvp_t = clock64();
 #define CVP_END(acc) { const long long cvp_n = clock64(); acc += cvp_n - cvp_t; cvp_t = cvp_n; }
 #else
@@ -346,23 +398,108 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
       return JUMPS ? q.t : (float)((double)s.T * (double)k / (double)n);  // partition(T, n, 'left')
     };
     auto is_active = [&](const Path& q, int k) { return q.valid && k < kcap && (JUMPS ? q.t < s.T : true); };
-    // my st.shared -> visible to the tensor core; my tcgen05.ld -> ordered before the next MMA; tell the issuer
-    auto operands_ready = [&](int tl) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // my tcgen05.ld / tcgen05.st have completed (tmem_wait_*) -> ordered before the issuer's next MMA.  One arrival
+    // per warp (128 arrivals on one mbarrier word serialise): every lane fences, the warp converges, lane 0 arrives.
+    auto release = [&]() {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar_full + 8 * tl);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(bar_full);
     };
-    // round of tile tl finished?  returns false when the issuer retired the tile instead
-    auto wait_round = [&](int tl) -> bool {
-      mbar_wait(bar_done + 8 * tl, ph_done[tl]);
-      ph_done[tl] ^= 1u;
+    // phase finished?
+    auto wait_phase = [&]() {
+      mbar_wait(bar_done, ph_done);
+      ph_done ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      return flags[2 * kCvTiles + tl] != 0;
     };
-    const uint32_t my_row_f = sbase + kCvOffA + (uint32_t)mine * (2 * kCvABytes) + row * 16, my_row_g = my_row_f + kCvABytes;
+    // first phase of a step: false when the issuer retired the tile instead (no active path left)
+    auto wait_step_start = [&]() -> bool {
+      wait_phase();
+      return flags[2 * kCvTiles + mine] != 0;
+    };
+    const uint32_t tl_lane = tile_cols + ((uint32_t)(quad * 32) << 16);  // my lanes, my tile's columns
+    const uint32_t t_d = tl_lane + kCvColD, t_af = tl_lane + kCvColAf, t_ag = tl_lane + kCvColAg;
+    // hidden-layer epilogue of one net: D -> registers, ReLU/bf16 -> the net's next activation vector.  EARLY: D is
+    // released right after the load, so the tensor core runs the other net's phase during the conversion (the vector
+    // that phase consumes was stored one phase ago); otherwise the arrival follows the store.
+    auto hidden_epilogue = [&](uint32_t ta, bool early) {
+      if (narrow) {
+        CvAccRow<true> d;
+        d.load(t_d);
+        if (early) release();
+        d.store_relu(ta);
+      } else {
+        CvAccRow<false> d;
+        d.load(t_d);
+        if (early) release();
+        d.store_relu(ta);
+      }
+      tmem_wait_st();
+      if (!early) release();
+    };
+    // One iteration of the path (solvers.py:182-225) and the weights its control-variate terms carry:
+    //   cvsum += cf * f(t_k, x_k) + cg * g(t_k, left_k)   with  cf = D dW,  cg = D (J_prev - rate E[J] dt)
+    // (integrate_cv varred.py:202-214, :124, :126-127).  Nothing here depends on the nets, so it runs while the
+    // tensor core works on the first phases of the step.
+    float cf = 0.0f, cg = 0.0f;
+    bool cv_live = false;  // the path was active in the iteration just advanced (finished paths add nothing)
+    auto advance_path = [&](int k) {
+      const bool active = is_active(p, k);
+      const float t_in = t_input(p, k);
+      // this thread's Brownian normal for iteration k (one Philox block serves 4 iterations)
+      if ((k & 3) == 0) {
+        if constexpr (!INJECT) {
+          uint32_t o[4];
+          philox4x32_10((uint32_t)(k >> 2), STREAM_DIFFUSION, p.plo, p.phi, keys, o);
+          box_muller(o[0], o[1], p.zbuf[0], p.zbuf[1]);
+          box_muller(o[2], o[3], p.zbuf[2], p.zbuf[3]);
+        }
+      }
+      float z;
+      if constexpr (INJECT) {
+        z = (p.valid && k < inj.K) ? inj.z[p.i * (uint64_t)inj.K + k] : 0.0f;
+      } else {
+        z = p.zbuf[0];
+        p.zbuf[0] = p.zbuf[1]; p.zbuf[1] = p.zbuf[2]; p.zbuf[2] = p.zbuf[3];
+      }
+      cf = 0.0f;
+      cg = 0.0f;
+      cv_live = active;
+      if (active) {
+        const float D = fast_ex2(-t_in * cv.disc_rate_l2e);
+        float dt, sq;
+        float tau = 0.0f;
+        if constexpr (JUMPS) {
+          p.src.begin_iter(s, keys, k);
+          p.src.advance(s, keys, p.need_pop);
+          tau = p.src.tau;
+          dt = fmaxf(fminf(s.h0, fminf(tau, s.T) - p.t), 0.0f);  // stateless mesh, see jump.cuh
+          sq = fast_sqrt(dt);
+        } else {
+          dt = s.h0;
+          sq = s.sqrt_h0;
+        }
+        float xv[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f}, xo[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
+        float w1[kMaxDim] = {z, 0.0f, 0.0f, 0.0f}, w2[kMaxDim] = {0.0f, 0.0f, 0.0f, 0.0f};
+        euler_step<C>(s, xv, dt, sq, w1, w2);
+        cf = D * (z * sq);                                         // f dW
+        if constexpr (JUMPS) {
+          cg = D * (k < cv.last_interval ? fmaf(cv.comp_c, dt, p.Jprev) : p.Jprev);  // g J - rate E[J] g dt
+          p.t += dt;
+          p.left = xv[0];
+          const bool hit = fabsf(tau - p.t) <= fmaf(fabsf(p.t), 1e-5f, 1e-12f);
+          const float Jc = hit ? p.src.mark(s, k) : 0.0f;
+          if (s.exact_jumps) xo[0] = xv[0];
+          add_jump<C>(s, xv, xo, Jc);
+          p.Jprev = Jc;
+          p.need_pop = hit;
+        }
+        p.x = xv[0];
+        p.own_iters = k + 1;
+      }
+    };
 
     for (uint64_t pair = blockIdx.x; pair * kCvTiles < n_tiles; pair += gridDim.x) {
-      // ---- state 0 of my path -> first-layer operands of my tile ------------------------------------------------
+      // ---- state 0 of my path -> first-layer activation vectors of my tile --------------------------------------
       p.i = (pair * kCvTiles + mine) * kCvRows + row;
       p.valid = p.i < rg.n_paths;
       {
@@ -383,113 +520,47 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
         if constexpr (INJECT) p.src.init(s, inj, p.valid ? p.i : 0);
         else p.src.init(p.plo, p.phi);
       }
-      write_input_row(my_row_f, t_input(p, 0), p.x);
-      if (JUMPS) write_input_row(my_row_g, t_input(p, 0), p.left);
+      write_input_row(t_af, t_input(p, 0), p.x);
+      if (JUMPS) write_input_row(t_ag, t_input(p, 0), p.left);
+      tmem_wait_st();
       if (is_active(p, 0)) flags[mine * 2 + 0] = 1;
-      bool live[kCvTiles];
-#pragma unroll
-      for (int tl = 0; tl < kCvTiles; ++tl) {
-        operands_ready(tl);
-        live[tl] = true;
-      }
+      release();
 
-      for (int k = 0; live[0] || live[1]; ++k) {
+      for (int k = 0;; ++k) {
+        CVP_BEGIN
+        if (!wait_step_start()) break;  // no active path was left in the tile: the issuer retired it
+        CVP_END(prof_wait)
+        // ---- hidden layers 1-3 of f (and g): six (three) phases; the last one keeps D until its vector is stored,
+        // because the head phase consumes the vectors of BOTH nets
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-#pragma unroll
-          for (int tl = 0; tl < kCvTiles; ++tl) {
-            if (!live[tl]) continue;
-            const uint32_t tacc_f = tlane + (uint32_t)tl * 128u, tacc_g = tacc_f + 64;
-            const uint32_t a_row_f = sbase + kCvOffA + (uint32_t)tl * (2 * kCvABytes) + row * 16, a_row_g = a_row_f + kCvABytes;
-            CVP_BEGIN
-            const bool ok = wait_round(tl);
-            CVP_END(prof_wait)
-#ifdef SDEMC_CV_PROFILE
-            ++prof_rounds;
-#endif
-            if (r == 0 && !ok) {  // no active path was left in the tile: the issuer retired it
-              live[tl] = false;
-              continue;
-            }
-            if (r < 3) {
-              // hidden layer r+1: accumulators -> ReLU -> bf16 -> A operand of the next round; this thread converts
-              // columns 32*mine .. 32*mine+31 of its row, its partner warp (same quadrant) the other half
-              hidden_epilogue_half(tacc_f + 32 * mine, a_row_f + mine * 4 * (kCvRows * 16));
-              if (JUMPS) hidden_epilogue_half(tacc_g + 32 * mine, a_row_g + mine * 4 * (kCvRows * 16));
-              CVP_END(prof_epi)
-              operands_ready(tl);
-              CVP_END(prof_ready)
-              continue;
-            }
-            if (mine != tl) {  // the owners of this tile advance their paths
-              operands_ready(tl);
-              continue;
-            }
-            // ---- r == 3: both nets evaluated at the state of index k -> advance my path by one iteration --------
-            const float fval = tmem_ld1(tacc_f);
-            const float gval = JUMPS ? tmem_ld1(tacc_g) : 0.0f;
-            const bool active = is_active(p, k);
-            const float t_in = t_input(p, k);
-            // this thread's Brownian normal for iteration k (one Philox block serves 4 iterations)
-            if ((k & 3) == 0) {
-              if constexpr (!INJECT) {
-                uint32_t o[4];
-                philox4x32_10((uint32_t)(k >> 2), STREAM_DIFFUSION, p.plo, p.phi, keys, o);
-                box_muller(o[0], o[1], p.zbuf[0], p.zbuf[1]);
-                box_muller(o[2], o[3], p.zbuf[2], p.zbuf[3]);
-              }
-            }
-            float z;
-            if constexpr (INJECT) {
-              z = (p.valid && k < inj.K) ? inj.z[p.i * (uint64_t)inj.K + k] : 0.0f;
-            } else {
-              z = p.zbuf[0];
-              p.zbuf[0] = p.zbuf[1]; p.zbuf[1] = p.zbuf[2]; p.zbuf[2] = p.zbuf[3];
-            }
-            if (active) {
-              const float D = fast_ex2(-t_in * cv.disc_rate_l2e);
-              float dt, sq;
-              float tau = 0.0f;
-              if constexpr (JUMPS) {
-                p.src.begin_iter(s, keys, k);
-                p.src.advance(s, keys, p.need_pop);
-                tau = p.src.tau;
-                dt = fmaxf(fminf(s.h0, fminf(tau, s.T) - p.t), 0.0f);  // stateless mesh, see jump.cuh
-                sq = fast_sqrt(dt);
-              } else {
-                dt = s.h0;
-                sq = s.sqrt_h0;
-              }
-              const float dW = z * sq;
-              float xv[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f}, xo[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
-              float w1[kMaxDim] = {z, 0.0f, 0.0f, 0.0f}, w2[kMaxDim] = {0.0f, 0.0f, 0.0f, 0.0f};
-              euler_step<C>(s, xv, dt, sq, w1, w2);
-              float c = fval * dW;                                     // f dW           (integrate_cv varred.py:202-214)
-              if constexpr (JUMPS) {
-                c = fmaf(gval, p.Jprev, c);                            // g J            (varred.py:124)
-                if (k < cv.last_interval) c = fmaf(cv.comp_c * gval, dt, c);   // - rate E[J] g dt (varred.py:126-127)
-                p.t += dt;
-                p.left = xv[0];
-                const bool hit = fabsf(tau - p.t) <= fmaf(fabsf(p.t), 1e-5f, 1e-12f);
-                const float Jc = hit ? p.src.mark(s, k) : 0.0f;
-                if (s.exact_jumps) xo[0] = xv[0];
-                add_jump<C>(s, xv, xo, Jc);
-                p.Jprev = Jc;
-                p.need_pop = hit;
-              }
-              p.x = xv[0];
-              p.cvsum = fmaf(c, D, p.cvsum);
-              p.own_iters = k + 1;
-            }
-            // first-layer operands of state k+1; the issuer starts the next step if any path of the tile goes on
-            write_input_row(a_row_f, t_input(p, k + 1), p.x);
-            if (JUMPS) write_input_row(a_row_g, t_input(p, k + 1), p.left);
-            if (is_active(p, k + 1)) flags[tl * 2 + ((k + 1) & 1)] = 1;
-            CVP_END(prof_adv)
-            operands_ready(tl);
-            CVP_END(prof_ready)
+        for (int ph = 0; ph < 3 * NETS; ++ph) {
+          hidden_epilogue(ph % NETS ? t_ag : t_af, JUMPS && ph < 3 * NETS - 1);
+          if (ph == 0) advance_path(k);  // state k+1, off the critical path
+          CVP_END(prof_epi)
+          wait_phase();
+          CVP_END(prof_wait)
+        }
+        // ---- heads: both nets evaluated at the state of index k ---------------------------------------------------
+        {
+          uint32_t hf, hg = 0u;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(hf) : "r"(t_d));
+          if (JUMPS) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(hg) : "r"(t_d + kCvHeadN));
+          tmem_wait_ld();
+          if (cv_live) {
+            p.cvsum = fmaf(cf, __uint_as_float(hf), p.cvsum);
+            if (JUMPS) p.cvsum = fmaf(cg, __uint_as_float(hg), p.cvsum);
           }
         }
+        // first-layer activation vectors of state k+1; the issuer starts the next step if any path of the tile goes on
+        write_input_row(t_af, t_input(p, k + 1), p.x);
+        if (JUMPS) write_input_row(t_ag, t_input(p, k + 1), p.left);
+        tmem_wait_st();
+        if (is_active(p, k + 1)) flags[mine * 2 + ((k + 1) & 1)] = 1;
+        release();
+        CVP_END(prof_adv)
+#ifdef SDEMC_CV_PROFILE
+        ++prof_steps;
+#endif
       }
 
       if (p.valid) {
@@ -502,9 +573,9 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
     }
 #ifdef SDEMC_CV_PROFILE
     if (blockIdx.x == 0 && (tid & 31) == 0)
-      printf("cvprof warp %d: total %lld clk, rounds %lld; per round: wait %.0f epi %.0f ready %.0f adv %.0f\n", warp,
-             clock64() - prof_t0, prof_rounds, (double)prof_wait / prof_rounds, (double)prof_epi / prof_rounds,
-             (double)prof_ready / prof_rounds, (double)prof_adv / prof_rounds);
+      printf("cvprof warp %d: total %lld clk, steps %lld; per step: wait %.0f epilogues %.0f advance %.0f\n", warp,
+             clock64() - prof_t0, prof_steps, (double)prof_wait / prof_steps, (double)prof_epi / prof_steps,
+             (double)prof_adv / prof_steps);
 #endif
   }
 
