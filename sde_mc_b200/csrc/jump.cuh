@@ -286,8 +286,16 @@ constexpr int kJumpStoreBlock = 128;  // threads per CTA of the storing kernels 
 #ifndef SDEMC_JUMP_MIN_BLOCKS
 #define SDEMC_JUMP_MIN_BLOCKS 4  // <= 64 registers per thread: 32 resident warps per SM
 #endif
+// Resident CTAs the register budget is sized for.  The dense multi-dimensional models (Levy 2-D: ~25 live parameters,
+// three normals and a four-branch inverse cdf per iteration) need ~110 registers; capped at 64 ptxas re-reads its
+// parameters with ~15 LDC per iteration (ADU pipe 71 % busy, profiles/r01_ncu_levy2d.*).  Measured on Levy 2-D:
+// 8.2e10 path-steps/s at 4 or 3 CTAs per SM, 8.9e10 at 2.
 template <class C, int JSRC, bool STORE>
-__global__ void __launch_bounds__(256, STORE ? SDEMC_JUMP_STORE_MINB : SDEMC_JUMP_MIN_BLOCKS) jump_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+constexpr int jump_min_blocks() {
+  return STORE ? SDEMC_JUMP_STORE_MINB : ((JSRC == JSRC_INLINE && C::DIM >= 2) ? 2 : SDEMC_JUMP_MIN_BLOCKS);
+}
+template <class C, int JSRC, bool STORE>
+__global__ void __launch_bounds__(256, jump_min_blocks<C, JSRC, STORE>()) jump_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                    const PhiloxKeys keys, const DevInject inj, const DevOut out,
                                                    const int qdepth, double* __restrict__ d_moments,
                                                    void* __restrict__ d_ws) {

@@ -15,8 +15,9 @@
 
 namespace sdemc {
 
+// 3 CTAs per SM: 80 registers keep the per-path setup free of spills (measured +5 % on the C5 pass against 4)
 template <class C>
-__global__ void __launch_bounds__(256, SDEMC_JUMP_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, 3)
     jump_flat_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys,
                      double* __restrict__ d_moments, void* __restrict__ d_ws) {
   constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M, MARKS = C::MARKS;
