@@ -55,8 +55,8 @@ OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0, "mlmc": 40.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of the workload's kernel, per launch, from the `ncu --set full` captures
 # in profiles/r01_ncu_<workload>.summary.txt (moments kernels touch HBM only for code, parameters and the per-CTA
 # partials; the storing kernels write their trajectories once: 1.006x / 1.067x the algorithmic bytes)
-NCU_DRAM_BYTES_PER_LAUNCH = {"gbm": 351488.0, "merton": 29696.0, "levy2d": 68096.0, "merton_cv": 315648.0,
-                             "gbm_store": 8.127e9 + 1.27e8, "merton_store": 5.394306e9 + 3.16317e8, "mlmc": None}
+NCU_DRAM_BYTES_PER_LAUNCH = {"gbm": 16896.0, "merton": 30208.0, "levy2d": 371456.0, "merton_cv": 165120.0,
+                             "gbm_store": 8.128509e9 + 1.26625e8, "merton_store": 5.394213e9 + 3.1638e8, "mlmc": 24832.0}
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 
 

@@ -11,13 +11,25 @@ namespace sdemc {
 #ifndef SDEMC_DIFF_MIN_BLOCKS
 #define SDEMC_DIFF_MIN_BLOCKS 1
 #endif
+#ifndef SDEMC_DIFF_STORE_MINB
+#define SDEMC_DIFF_STORE_MINB 1
+#endif
+// The 1-D single-driver moments kernel (GBM, the default benchmark) is bound by the XU pipe (two MUFU per normal) and
+// fits 40 registers without spills: 6 resident CTAs per SM keep more MUFU operations in flight than the 4 the
+// unconstrained 56-register build gets (measured 1.586e12 vs 1.557e12 path-steps/s; 5 CTAs 1.569e12, 8 with spills 1.58e12)
+#ifndef SDEMC_DIFF_1D_MIN_BLOCKS
+#define SDEMC_DIFF_1D_MIN_BLOCKS 6
+#endif
+template <class C, bool HESTON, bool INJECT, bool STORE>
+constexpr int diffusion_min_blocks() {
+  if (STORE) return SDEMC_DIFF_STORE_MINB;
+  if (INJECT) return 1;
+  return (C::DIM == 1 && C::M == 1 && !HESTON && C::FAMILY != SDEMC_FAMILY_USER) ? SDEMC_DIFF_1D_MIN_BLOCKS : SDEMC_DIFF_MIN_BLOCKS;
+}
 // staging tile of the path-storing mode: 32 elements per path and flush; a step group stages up to
 // steps_per_group * max(dim, increments per step) elements
 #ifndef SDEMC_DIFF_STORE_TILE
 #define SDEMC_DIFF_STORE_TILE 32
-#endif
-#ifndef SDEMC_DIFF_STORE_MINB
-#define SDEMC_DIFF_STORE_MINB 1
 #endif
 template <class C>
 using DiffusionStoreWriter =
@@ -28,7 +40,7 @@ using DiffusionStoreWriter =
 constexpr int kDiffusionStoreBlock = 128;  // threads per CTA of the storing kernels (shared tiles limit residency)
 
 template <class C, bool HESTON, bool INJECT, bool STORE>
-__global__ void __launch_bounds__(256, STORE ? SDEMC_DIFF_STORE_MINB : (INJECT ? 1 : SDEMC_DIFF_MIN_BLOCKS)) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+__global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, STORE>()) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                         const PhiloxKeys keys, const DevInject inj, const DevOut out,
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
   constexpr int DIM = C::DIM, M = C::M, BASE = C::BASE;
