@@ -57,6 +57,14 @@ OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0, "mlmc": 40.0}
 # partials; the storing kernels write their trajectories once: 1.006x / 1.067x the algorithmic bytes)
 NCU_DRAM_BYTES_PER_LAUNCH = {"gbm": 16896.0, "merton": 30208.0, "levy2d": 371456.0, "merton_cv": 165120.0,
                              "gbm_store": 8.128509e9 + 1.26625e8, "merton_store": 5.394213e9 + 3.1638e8, "mlmc": 24832.0}
+# pipe utilisation of the same kernels in those captures (percent of peak while active): issue slots, FMA, ALU, XU and
+# tensor pipes.  The canonical op counts above are larger than what the SASS executes (e.g. GBM 23 vs 14.7
+# instructions per path-step), so `frac` can exceed the issue utilisation; both are reported.
+NCU_PIPE_PCT = {"gbm": dict(issue=64.9, fma=31.2, alu=41.2, xu=69.6), "merton": dict(issue=68.2, fma=30.6, alu=48.1, xu=42.7),
+                "levy2d": dict(issue=66.4, fma=31.9, alu=46.3, xu=47.0),
+                "merton_cv": dict(issue=44.5, fma=5.7, alu=45.5, xu=6.3, tensor=42.4),
+                "mlmc": dict(issue=66.4, fma=28.1, alu=49.5, xu=39.8), "gbm_store": dict(issue=37.3, fma=16.7, alu=24.6, xu=21.6),
+                "merton_store": dict(issue=48.2, fma=15.3, alu=28.0, xu=9.4)}
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 
 
@@ -252,10 +260,7 @@ def main():
 
     def mlmc_step():
         # all levels queued back to back (each rank 1/G of every level), moments stay on the device
-        pend = [M._level_moments(solver, payoff, discounter, mlmc_trials[0], MLMC_LEVELS[0], 0)]
-        for li in range(1, len(MLMC_LEVELS)):
-            pend.append(M._level_moments(solver, payoff, discounter, mlmc_trials[li], MLMC_LEVELS[li], MLMC_LEVELS[li - 1]))
-        return pend
+        return M._all_levels(solver, payoff, discounter, [int(v) for v in mlmc_trials], MLMC_LEVELS)
 
     def store_step():
         # the solve() contract: trajectories in the reference's layouts, resident in HBM (each rank its own paths)
@@ -371,6 +376,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak, "unit": "Tlaneop/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload),
+                         "ncu_pipe_pct": NCU_PIPE_PCT.get(args.workload),
                          "ops_per_path_step": OPS_PER_PATH_STEP[args.workload],
                          "peak_def": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock sampled during the run)"
                                      % (sm_count, mhz),

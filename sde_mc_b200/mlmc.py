@@ -35,13 +35,45 @@ def _level_moments(solver, payoff, discounter, trials, fine, coarse):
     return mom
 
 
+_level_streams = {}
+
+
+def _all_levels(solver, payoff, discounter, trials, levels):
+    """Queue one launch per level and return their Moments.  The levels are independent, so each goes to a stream of
+    its own (forked from and joined back into the current stream): level 0 fills the GPU first, the small fine levels
+    -- a wave or two of long serial paths each -- then overlap instead of running their tails one after the other.
+    SDEMC_MLMC_STREAMS=0 keeps everything on the current stream."""
+    import os
+    trials = [trials] * len(levels) if not isinstance(trials, (list, tuple)) else trials
+    dev = solver._compute_device()
+    coarse = [0] + list(levels[:-1])
+    if os.environ.get("SDEMC_MLMC_STREAMS", "1") == "0" or len(levels) < 2:
+        return [_level_moments(solver, payoff, discounter, n, f, c) for n, f, c in zip(trials, levels, coarse)]
+    with torch.cuda.device(dev):
+        pool = _level_streams.setdefault(dev, [])
+        while len(pool) < len(levels):
+            pool.append(torch.cuda.Stream(device=dev))
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        pending = []
+        for side, n, f, c in zip(pool, trials, levels, coarse):
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                mom = _level_moments(solver, payoff, discounter, n, f, c)
+                mom.buf.record_stream(cur)       # read (and possibly freed) on the caller's stream
+            join = torch.cuda.Event()
+            join.record(side)
+            cur.wait_event(join)
+            pending.append(mom)
+    return pending
+
+
 def mc_multilevel(trials, levels, solver, payoff, discounter, bs=None):
     """MLMC estimate  sum_l E[P_l - P_{l-1}]  with trials[l] coupled pairs on level l (mlmc.py:7-74).
     `bs` is accepted for compatibility; nothing is stored so no batching is needed."""
     start = time.time()
-    pending = [_level_moments(solver, payoff, discounter, trials[0], levels[0], 0)]
-    for i in range(1, len(levels)):
-        pending.append(_level_moments(solver, payoff, discounter, trials[i], levels[i], levels[i - 1]))
+    pending = _all_levels(solver, payoff, discounter, [int(n) for n in trials], levels)
     total_mean, total_var = 0.0, 0.0
     for n, mom in zip(trials, pending):          # one host read per level, after all launches are queued
         m = mom.read()
@@ -54,9 +86,7 @@ def mc_multilevel(trials, levels, solver, payoff, discounter, bs=None):
 def get_optimal_trials(trials, levels, epsilon, solver, payoff, discounter):
     """Pilot of `trials` pairs per level -> N_l = ceil(1.96^2/eps^2 sqrt(V_l h_l) sum_k sqrt(V_k / h_k))
     (mlmc.py:77-97; eps is a 95% half-width)."""
-    pending = [_level_moments(solver, payoff, discounter, trials, levels[0], 0)]
-    for i in range(1, len(levels)):
-        pending.append(_level_moments(solver, payoff, discounter, trials, levels[i], levels[i - 1]))
+    pending = _all_levels(solver, payoff, discounter, [int(trials)] * len(levels), levels)
     variances = []
     for mom in pending:
         m = mom.read()
