@@ -14,11 +14,12 @@ namespace sdemc {
 #ifndef SDEMC_DIFF_STORE_MINB
 #define SDEMC_DIFF_STORE_MINB 1
 #endif
-// The 1-D single-driver moments kernel (GBM, the default benchmark) is bound by the XU pipe (two MUFU per normal) and
-// fits 40 registers without spills: 6 resident CTAs per SM keep more MUFU operations in flight than the 4 the
-// unconstrained 56-register build gets (measured 1.586e12 vs 1.557e12 path-steps/s; 5 CTAs 1.569e12, 8 with spills 1.58e12)
+// The 1-D single-driver moments kernel (GBM, the default benchmark) is bound by the XU pipe (two MUFU per normal).
+// Measured, path-steps/s: plain loop 1.557e12 at 4 CTAs per SM (56 registers), 1.569e12 at 5, 1.586e12 at 6 (40
+// registers), 1.58e12 at 8 (spills); with the Philox rounds of the next block software-pipelined against the
+// Box-Muller transcendentals of the current one (below) 1.614e12 at 4, **1.657e12 at 5 (47 registers)**, 1.538e12 at 6.
 #ifndef SDEMC_DIFF_1D_MIN_BLOCKS
-#define SDEMC_DIFF_1D_MIN_BLOCKS 6
+#define SDEMC_DIFF_1D_MIN_BLOCKS 5
 #endif
 template <class C, bool HESTON, bool INJECT, bool STORE>
 constexpr int diffusion_min_blocks() {
@@ -83,9 +84,7 @@ __global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, S
       // 1-D single-driver moments path (GBM / log-GBM): sigma sqrt(h) is folded into the Box-Muller radius and
       // full Philox blocks (6 steps) run without per-step predicates: 2 FFMA per step on top of the normal.
       const int nb_full = S / SPB;
-      for (int b = 0; b < nb_full; ++b) {
-        uint32_t o[4];
-        philox4x32_10((uint32_t)b, STREAM_DIFFUSION, plo, phi, keys, o);
+      auto six_steps = [&](const uint32_t(&o)[4]) {
         float r[3], c[3], sn[3];
         philox_polar3(o, s.neg2ln2_b1s2, r, c, sn);
 #pragma unroll
@@ -98,7 +97,27 @@ __global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, S
             x[0] += g0 + g1;
           }
         }
+      };
+#ifndef SDEMC_DIFF_NO_PIPELINE
+      // software pipeline: the Philox rounds of block b+1 (ALU / FMA pipes) are independent of the Box-Muller
+      // transcendentals of block b (XU pipe), so ptxas can interleave them inside one loop body
+      uint32_t oa[4], ob[4];
+      philox4x32_10(0u, STREAM_DIFFUSION, plo, phi, keys, oa);
+      int b = 0;
+      for (; b + 2 <= nb_full; b += 2) {
+        philox4x32_10((uint32_t)(b + 1), STREAM_DIFFUSION, plo, phi, keys, ob);
+        six_steps(oa);
+        philox4x32_10((uint32_t)(b + 2), STREAM_DIFFUSION, plo, phi, keys, oa);
+        six_steps(ob);
       }
+      if (b < nb_full) six_steps(oa);
+#else
+      for (int b = 0; b < nb_full; ++b) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)b, STREAM_DIFFUSION, plo, phi, keys, o);
+        six_steps(o);
+      }
+#endif
       b_first = nb_full;  // the generic loop below finishes the S % 6 remaining steps
     }
 
