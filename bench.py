@@ -24,6 +24,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL prints
+# its version banner there when the first communicator is created), so fd 1 is pointed at stderr for the whole run
+# and the result line goes to the saved original descriptor.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (line + "\n").encode())
 
 # canonical algorithmic work per nominal path-step, in FP32/ALU/XU lane-operations (SURVEY.md section 8d,
 # restated in DESIGN.md): one N(0,1) = 21 ops; GBM Euler step 2 ops; Merton jump-adapted iteration 39 ops x 1.03.
@@ -216,7 +225,7 @@ def main():
             return 0
         k, wu = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
         value, sec, info = cpu_reference(args.workload, k, wu)
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": "path_steps_per_sec", "value": value, "unit": "path-steps/s",
             "n_gpus": args.gpus, "steps": k, "warmup": wu, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -437,7 +446,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             _, _, info = cpu_reference(args.workload, 2, 1)
             out["cpu_baseline"] = info
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
