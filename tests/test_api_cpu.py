@@ -245,3 +245,24 @@ def test_no_cpu_fallback():
         solver.solve(bs=4)
     with pytest.raises(L.SdemcError):
         sm.mc_simple(100, solver, sm.EuroCall(1.0), sm.ConstantShortRate(0.02), bs=10)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: rank 0 prints ONE JSON line on stdout (everything else -- progress, native libraries such as
+    NCCL's version banner -- goes to stderr).  The reference arm runs without a GPU: the reference's CPU algorithm
+    (oracle/torch_port.py) on a bounded sample of the default workload."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "path_steps_per_sec" and d["unit"] == "path-steps/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"] == "gbm_1d_eurocall_euler_1e9x252"
