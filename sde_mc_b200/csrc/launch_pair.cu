@@ -1,4 +1,6 @@
 // launch_pair.cu -- instantiation + dispatch of the MLMC pair kernels (pair.cuh)
+#include <cmath>
+#include <cstdlib>
 #include <type_traits>
 
 #include "launch.cuh"
@@ -20,8 +22,28 @@ int run(Kernel kernel, const LaunchArgs& a, int fine, int coarse, float* d_termi
   return SDEMC_OK;
 }
 
+// moments-only pairs with persistent lanes (pair.cuh): same rule as launch_jump.cu:want_flat with the pair's
+// coarse + rate T outer iterations.  SDEMC_PAIR_FLAT=0/1 overrides (benchmarks).
+bool want_flat_pair(const DevSde& s, int coarse) {
+  if (const char* e = getenv("SDEMC_PAIR_FLAT")) return atoi(e) != 0;
+  const double lam_T = (double)s.rate * (double)s.T;
+  return 2.1 * std::sqrt(lam_T) > 0.2 * ((double)coarse + lam_T);
+}
+
+template <class C>
+int run_flat(const LaunchArgs& a, int fine, int coarse) {
+  auto kernel = jump_pair_flat_kernel<C>;
+  int grid = 0;
+  int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
+  if (rc != SDEMC_OK) return rc;
+  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, fine, coarse, a.d_moments, a.d_ws);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+
 template <class C>
 int jump_by_mode(const LaunchArgs& a, int fine, int coarse, float* t) {
+  if (!a.use_inject && t == nullptr && want_flat_pair(a.sde, coarse)) return run_flat<C>(a, fine, coarse);
   return a.use_inject ? run(jump_pair_kernel<C, true>, a, fine, coarse, t) : run(jump_pair_kernel<C, false>, a, fine, coarse, t);
 }
 template <class C>

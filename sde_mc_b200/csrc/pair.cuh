@@ -51,14 +51,99 @@ struct DevPairOut {
   float* terminal;  // (n, 2, dim): fine, coarse terminal states (parity mode) or nullptr
 };
 
+// state of one coupled (fine, coarse) pair of jump-adapted paths
+template <class C, bool INJECT>
+struct PairPath {
+  static constexpr int NZ = C::BASE + (C::M == 2 ? 1 : 0);
+  float xf[kMaxDim], xc[kMaxDim];
+  float tf, tc;
+  int k;
+  bool need_pop;
+  typename std::conditional<INJECT, InjectJumps<C::MARKS>, InlineJumps<C::MARKS>>::type src;
+  NormalStream<NZ> normals;
+
+  __device__ __forceinline__ void start(const DevSde& s, const DevInject& inj, uint64_t i, uint32_t plo, uint32_t phi) {
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) xf[d] = xc[d] = d < C::DIM ? s.x0[d] : 0.0f;
+    tf = 0.0f;
+    tc = 0.0f;
+    k = 0;
+    need_pop = true;
+    if constexpr (INJECT) src.init(s, inj, i);
+    else src.init(plo, phi);
+    normals.init(plo, phi);
+  }
+};
+
+// one outer iteration of the coupled loop solvers.py:254-305: `factor` fine sub-steps, one coarse step on the summed
+// increments, the shared jump
+template <class C, bool INJECT>
+__device__ __forceinline__ void pair_iteration(const DevSde& s, const PhiloxKeys& keys, const DevInject& inj,
+                                               PairPath<C, INJECT>& p, uint64_t i, int factor, float hf0, float hc0) {
+  constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M;
+  constexpr int NZ = PairPath<C, INJECT>::NZ;
+  float xof[kMaxDim], xoc[kMaxDim];
+#pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) xof[d] = p.xf[d];
+  p.src.begin_iter(s, keys, p.k);
+  p.src.advance(s, keys, p.need_pop);
+  const float tau = p.src.tau;
+  float s1[kMaxDim], s2[kMaxDim];
+#pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) s1[d] = s2[d] = 0.0f;
+  for (int q = 0; q < factor; ++q) {                         // :259-278
+    const int sub = p.k * factor + q;
+    float zn[NZ];
+    if constexpr (!INJECT) {
+      p.normals.next(keys, zn);
+    } else {
+      const uint64_t zi = i * (uint64_t)inj.K * factor + sub;
+#pragma unroll
+      for (int d = 0; d < BASE; ++d) zn[d] = inj.z[zi * DIM + d];
+      if (M == 2) zn[BASE] = inj.zc[zi];
+    }
+    const float dt = fmaxf(fminf(hf0, fminf(tau, s.T) - p.tf), 0.0f);  // stateless mesh, see jump.cuh
+    const float sq = fast_sqrt(dt);
+    float z1[kMaxDim], w1[kMaxDim], w2[kMaxDim];
+#pragma unroll
+    for (int d = 0; d < BASE; ++d) z1[d] = zn[d];
+    correlate<C>(s, z1, w1);
+#pragma unroll
+    for (int d = 0; d < BASE; ++d) w2[d] = M == 2 ? zn[BASE] : 0.0f;
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) xof[d] = p.xf[d];      // state before the LAST fine sub-step (:275)
+    euler_step<C>(s, p.xf, dt, sq, w1, w2);
+    p.tf += dt;
+#pragma unroll
+    for (int d = 0; d < BASE; ++d) {
+      s1[d] = fmaf(w1[d], sq, s1[d]);
+      if (M == 2) s2[d] = fmaf(w2[d], sq, s2[d]);
+    }
+  }
+  const float dtc = fmaxf(fminf(hc0, fminf(tau, s.T) - p.tc), 0.0f);   // :282-286
+#pragma unroll
+  for (int d = 0; d < kMaxDim; ++d) xoc[d] = p.xc[d];
+  euler_step<C>(s, p.xc, dtc, 1.0f, s1, s2);
+  p.tc += dtc;
+  const bool hit = fabsf(tau - p.tf) <= fmaf(fabsf(p.tf), 1e-5f, 1e-12f);   // :291 (on the fine clock)
+  const float Jc = hit ? p.src.mark(s, p.k) : 0.0f;
+  if (s.exact_jumps) {
+    add_jump<C>(s, p.xf, p.xf, Jc);
+    add_jump<C>(s, p.xc, p.xc, Jc);
+  } else {
+    add_jump<C>(s, p.xf, xof, Jc);
+    add_jump<C>(s, p.xc, xoc, Jc);
+  }
+  p.need_pop = hit;
+  ++p.k;
+}
+
 template <class C, bool INJECT>
 __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                         const PhiloxKeys keys, const DevInject inj, const int fine,
                                                         const int coarse, const DevPairOut pout,
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
-  constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M, MARKS = C::MARKS;
-  constexpr int NZ = BASE + (M == 2 ? 1 : 0);
-  constexpr int BPS = (NZ + 3) / 4;
+  constexpr int DIM = C::DIM;
   const int factor = fine / coarse;                              // :231
   const float hf0 = (float)((double)s.T / (double)fine);         // :233
   const float hc0 = (float)factor * hf0;                         // :234
@@ -69,82 +154,68 @@ __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const De
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
     const uint64_t gp = rg.path_lo + i;
-    const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
-    float xf[kMaxDim], xc[kMaxDim], xof[kMaxDim], xoc[kMaxDim];
-#pragma unroll
-    for (int d = 0; d < kMaxDim; ++d) xf[d] = xc[d] = xof[d] = xoc[d] = d < DIM ? s.x0[d] : 0.0f;
-    float tf = 0.0f, tc = 0.0f;
-    int k = 0;
-    bool need_pop = true;
-    typename std::conditional<INJECT, InjectJumps<MARKS>, InlineJumps<MARKS>>::type src;
-    if constexpr (INJECT) src.init(s, inj, i);
-    else src.init(plo, phi);
-    NormalStream<NZ> normals;
-    normals.init(plo, phi);
-
-    while (tf < s.T && k < kcap) {                               // :254
-      src.begin_iter(s, keys, k);
-      src.advance(s, keys, need_pop);
-      const float tau = src.tau;
-      float s1[kMaxDim], s2[kMaxDim];
-#pragma unroll
-      for (int d = 0; d < kMaxDim; ++d) s1[d] = s2[d] = 0.0f;
-      for (int q = 0; q < factor; ++q) {                         // :259-278
-        const int sub = k * factor + q;
-        float zn[NZ];
-        if constexpr (!INJECT) {
-          normals.next(keys, zn);
-        } else {
-          const uint64_t zi = i * (uint64_t)inj.K * factor + sub;
-#pragma unroll
-          for (int d = 0; d < BASE; ++d) zn[d] = inj.z[zi * DIM + d];
-          if (M == 2) zn[BASE] = inj.zc[zi];
-        }
-        const float dt = fmaxf(fminf(hf0, fminf(tau, s.T) - tf), 0.0f);  // stateless mesh, see jump.cuh
-        const float sq = fast_sqrt(dt);
-        float z1[kMaxDim], w1[kMaxDim], w2[kMaxDim];
-#pragma unroll
-        for (int d = 0; d < BASE; ++d) z1[d] = zn[d];
-        correlate<C>(s, z1, w1);
-#pragma unroll
-        for (int d = 0; d < BASE; ++d) w2[d] = M == 2 ? zn[BASE] : 0.0f;
-#pragma unroll
-        for (int d = 0; d < kMaxDim; ++d) xof[d] = xf[d];        // state before the LAST fine sub-step (:275)
-        euler_step<C>(s, xf, dt, sq, w1, w2);
-        tf += dt;
-#pragma unroll
-        for (int d = 0; d < BASE; ++d) {
-          s1[d] = fmaf(w1[d], sq, s1[d]);
-          if (M == 2) s2[d] = fmaf(w2[d], sq, s2[d]);
-        }
-      }
-      const float dtc = fmaxf(fminf(hc0, fminf(tau, s.T) - tc), 0.0f);   // :282-286
-#pragma unroll
-      for (int d = 0; d < kMaxDim; ++d) xoc[d] = xc[d];
-      euler_step<C>(s, xc, dtc, 1.0f, s1, s2);
-      tc += dtc;
-      const bool hit = fabsf(tau - tf) <= fmaf(fabsf(tf), 1e-5f, 1e-12f);   // :291 (on the fine clock)
-      const float Jc = hit ? src.mark(s, k) : 0.0f;
-      if (s.exact_jumps) {
-        add_jump<C>(s, xf, xf, Jc);
-        add_jump<C>(s, xc, xc, Jc);
-      } else {
-        add_jump<C>(s, xf, xof, Jc);
-        add_jump<C>(s, xc, xoc, Jc);
-      }
-      need_pop = hit;
-      ++k;
-    }
+    PairPath<C, INJECT> p;
+    p.start(s, inj, i, (uint32_t)gp, (uint32_t)(gp >> 32));
+    while (p.tf < s.T && p.k < kcap) pair_iteration<C, INJECT>(s, keys, inj, p, i, factor, hf0, hc0);   // :254
 
     if (pout.terminal) {
 #pragma unroll
       for (int d = 0; d < DIM; ++d) {
-        pout.terminal[(i * 2 + 0) * DIM + d] = xf[d];
-        pout.terminal[(i * 2 + 1) * DIM + d] = xc[d];
+        pout.terminal[(i * 2 + 0) * DIM + d] = p.xf[d];
+        pout.terminal[(i * 2 + 1) * DIM + d] = p.xc[d];
       }
     }
-    const float diff = eval_payoff<DIM>(po, xf) - eval_payoff<DIM>(po, xc);
-    acc.add(diff, 0.0f, k * factor);
+    const float diff = eval_payoff<DIM>(po, p.xf) - eval_payoff<DIM>(po, p.xc);
+    acc.add(diff, 0.0f, p.k * factor);
+  }
+  block_reduce_and_publish(acc, d_moments, d_ws);
+}
+
+// The same pairs with persistent lanes (see jump_flat.cuh): a warp of jump_pair_kernel runs until its slowest lane is
+// done, which for the coarse levels (coarse + #jumps outer iterations with #jumps ~ Poisson(rate T)) is about twice
+// the mean.  Here a lane whose pair reached T starts its next pair at the next group boundary.  A group is six outer
+// iterations: an even number (a Philox block of jump candidates serves two iterations) that consumes whole Philox
+// blocks of normals for every factor and driver count, so all lanes refill together and every pair reads exactly the
+// counters it reads in jump_pair_kernel -- bit-identical pairs, only the order of the fp64 additions differs.
+template <class C>
+__global__ void __launch_bounds__(256) jump_pair_flat_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
+                                                             const PhiloxKeys keys, const int fine, const int coarse,
+                                                             double* __restrict__ d_moments, void* __restrict__ d_ws) {
+  constexpr int DIM = C::DIM;
+  constexpr int G = 6;
+  const int factor = fine / coarse;
+  const float hf0 = (float)((double)s.T / (double)fine);
+  const float hc0 = (float)factor * hf0;
+  const int kcap = 4 * (coarse + s.max_jumps) + 64;
+  DevInject no_inject;
+  no_inject.z = no_inject.zc = no_inject.jump_times = no_inject.marks = nullptr;
+  no_inject.K = 0;
+
+  Accum acc;
+  acc.zero();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = i < rg.n_paths;
+  PairPath<C, false> p;
+  {
+    const uint64_t gp = rg.path_lo + (live ? i : 0);
+    p.start(s, no_inject, i, (uint32_t)gp, (uint32_t)(gp >> 32));
+  }
+  while (live) {
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      if (p.tf < s.T && p.k < kcap) pair_iteration<C, false>(s, keys, no_inject, p, i, factor, hf0, hc0);
+    }
+    if (!(p.tf < s.T) || p.k >= kcap) {
+      const float diff = eval_payoff<DIM>(po, p.xf) - eval_payoff<DIM>(po, p.xc);
+      acc.add(diff, 0.0f, p.k * factor);
+      i += stride;
+      live = i < rg.n_paths;
+      if (live) {
+        const uint64_t gp = rg.path_lo + i;
+        p.start(s, no_inject, i, (uint32_t)gp, (uint32_t)(gp >> 32));
+      }
+    }
   }
   block_reduce_and_publish(acc, d_moments, d_ws);
 }

@@ -151,3 +151,31 @@ def test_short_path_kernel_matches_generic_kernel(case, monkeypatch):
     assert a["iters"] == b["iters"] and a["iters"] > n * steps
     for key in ("sum", "sumsq"):
         assert abs(a[key] - b[key]) <= 1e-11 * abs(a[key]), (key, a[key], b[key])
+
+
+@pytest.mark.parametrize("case", ["merton_2_1", "merton_8_4_exact", "merton_16_4", "levy2d_4_2_exact"])
+def test_persistent_lane_pair_kernel_matches_lockstep_pair_kernel(case, monkeypatch):
+    """jump_pair_flat_kernel (chosen for the coarse levels) simulates the SAME coupled pairs as jump_pair_kernel:
+    identical pair count and fine sub-step total, moments of P_f - P_c equal up to the fp64 summation order."""
+    from sde_mc_b200.mlmc import _level_moments
+    if case.startswith("merton"):
+        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+        payoff = sm.EuroCall(1.0)
+    else:
+        levy = sm.ExpExampleLevy(1, 1, .5, 2, .02, .3, .2, .05, dim=2)
+        sde = sm.LevySde(levy, torch.tensor([1., 1.]))
+        payoff = sm.Rainbow(1.0)
+    fine, coarse = {"merton_2_1": (2, 1), "merton_8_4_exact": (8, 4), "merton_16_4": (16, 4),
+                    "levy2d_4_2_exact": (4, 2)}[case]
+    n = 200_003
+    res = {}
+    for flat in ("0", "1"):
+        monkeypatch.setenv("SDEMC_PAIR_FLAT", flat)
+        solver = sm.JumpEulerSolver(sde, 3, coarse, device=DEV, exact_jumps=case.endswith("exact"), seed=11)
+        res[flat] = _level_moments(solver, payoff, sm.ConstantShortRate(0.02), n, fine, coarse).read()
+    a, b = res["0"], res["1"]
+    assert a["n"] == b["n"] == n
+    assert a["iters"] == b["iters"] and a["iters"] >= n * fine
+    assert a["sumsq"] > 0
+    for key in ("sum", "sumsq"):
+        assert abs(a[key] - b[key]) <= 1e-10 * max(abs(a[key]), a["sumsq"] ** 0.5), (key, a[key], b[key])
