@@ -8,8 +8,8 @@
 // the tile's 128 TMEM columns -- 64 fp32 accumulator columns D shared by both nets, 32 columns A_f and 32 columns
 // A_g holding the nets' current activation vectors as bf16 pairs (column c = units 2c, 2c+1).  Each time step evaluates
 //   Linear(2,H) ReLU Linear(H,H) ReLU Linear(H,H) ReLU Linear(H,1)         (nets.py:39-93, BN-free, H <= 63)
-// for both nets as EIGHT phases per tile, f and g alternating: (layer 1, f) (layer 1, g) (layer 2, f) ... (head, g),
-// each one `tcgen05.mma.cta_group::1.kind::f16 [D], [A_net], b_desc` chain (M=128; N=64,K=16 | N=64,K=64 | N=64,K=64 |
+// for both nets as SEVEN phases per tile, f and g alternating on D: (layer 1, f) (layer 1, g) (layer 2, f) (layer 2, g)
+// (layer 3, f) (layer 3, g) and the two heads together (D columns 0-15 and 16-31); a phase is one `tcgen05.mma.cta_group::1.kind::f16 [D], [A_net], b_desc` chain (M=128; N=64,K=16 | N=64,K=64 | N=64,K=64 |
 // N=16,K=64; bf16 in, fp32 accumulate) with the weights (B) in shared memory.  The four worker warps of a tile (one
 // per TMEM lane quadrant) read D with tcgen05.ld, release it, and while the tensor core already runs the OTHER
 // net's phase into D they apply ReLU, pack to bf16 and write the next activation vector back with tcgen05.st.
@@ -17,7 +17,7 @@
 // K=16 MMA pulls 4 KB of A and 2 KB of B through the tensor core's shared-memory port at 128 B/clk -- 48 clk for an
 // instruction whose math takes 32 -- and the epilogues write the same bytes through the LSU: ncu showed
 // l1tex__data_pipe_tc_wavefronts_mem_shared at 65 % and sm__pipe_tc_cycles_active at 79 % with the tensor math only
-// 36 % busy (profiles/r01_ncu_merton_cv.*).  From TMEM the A operand costs no shared-memory bandwidth at all, the
+// 36 % busy (profiles/r01_ncu_merton_cv_smemA.*).  From TMEM the A operand costs no shared-memory bandwidth at all, the
 // generic->async proxy fence of every round disappears, and sharing D between the nets keeps a tile at 128 columns,
 // so four tiles (2 CTAs x 2) are still resident per SM to hide each other's MMA / commit / wake-up latency.
 // Every tile is an independent chain with its own issuer warp; there is no CTA barrier in the step loop.
