@@ -55,6 +55,18 @@ int run_flat(const LaunchArgs& a) {
   return SDEMC_OK;
 }
 
+// 1-D lognormal-mark models: two iterations per Philox block, no alignment across the warp (jump_flat.cuh)
+template <class C>
+int run_flat1d(const LaunchArgs& a) {
+  auto kernel = jump_flat1d_kernel<C>;
+  int grid = 0;
+  int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
+  if (rc != SDEMC_OK) return rc;
+  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.d_moments, a.d_ws);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+
 // A warp of jump_kernel runs until its slowest lane is done: E[max of 32 Poisson(rate T)] exceeds the mean by about
 // 2.1 sqrt(rate T) iterations.  When that is more than a fifth of a path's num_steps + rate T iterations the
 // persistent-lane kernel wins (MLMC level 0: 2.1 * 1.7 / 4).  SDEMC_JUMP_FLAT=0/1 overrides (benchmarks).
@@ -71,7 +83,13 @@ int by_mode(const LaunchArgs& a) {
       return a.sde.exact_jumps ? run_1d<C, true>(a) : run_1d<C, false>(a);
   }
   if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;
-  if (a.flat && !a.store && a.qdepth == 0) return run_flat<C>(a);
+  if (a.flat && !a.store && a.qdepth == 0) {
+    if constexpr (C::DIM == 1 && C::M == 1 && !C::ASIAN && C::MARKS == SDEMC_MARKS_LOGNORMAL) {
+      const char* e = getenv("SDEMC_JUMP_FLAT_PACKED");  // 0: keep the streams of jump_kernel (aligned groups of six)
+      if (!e || atoi(e) != 0) return run_flat1d<C>(a);
+    }
+    return run_flat<C>(a);
+  }
   if (a.qdepth > 0) return a.store ? run<C, JSRC_QUEUE, true>(a) : run<C, JSRC_QUEUE, false>(a);
   return a.store ? run<C, JSRC_INLINE, true>(a) : run<C, JSRC_INLINE, false>(a);
 }

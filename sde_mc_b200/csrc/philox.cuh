@@ -21,7 +21,8 @@ struct PhiloxKeys {
 enum : uint32_t {
   STREAM_DIFFUSION = 0,   // Brownian unit normals, consumed in loop order
   STREAM_JUMP_QUEUE = 1,  // (gap, mark) pairs of the sparse-jump queue
-  STREAM_JUMP_INLINE = 2  // per-iteration (gap, mark) candidates of the dense-jump strategy
+  STREAM_JUMP_INLINE = 2, // per-iteration (gap, mark) candidates of the dense-jump strategy
+  STREAM_PACKED = 3       // jump_flat.cuh, 1-D short paths: normals, gaps and marks of two iterations in one block
 };
 
 __host__ inline PhiloxKeys make_philox_keys(uint64_t seed) {

@@ -138,6 +138,7 @@ def test_short_path_kernel_matches_generic_kernel(case, monkeypatch):
     n = 300_001  # ragged: the last warp is partial and lanes run out of paths at different times
     lib = L.load()
     res = {}
+    monkeypatch.setenv("SDEMC_JUMP_FLAT_PACKED", "0")   # the variant that keeps jump_kernel's streams
     for flat in ("0", "1"):
         monkeypatch.setenv("SDEMC_JUMP_FLAT", flat)
         with torch.cuda.device(DEV):
@@ -179,3 +180,44 @@ def test_persistent_lane_pair_kernel_matches_lockstep_pair_kernel(case, monkeypa
     assert a["sumsq"] > 0
     for key in ("sum", "sumsq"):
         assert abs(a[key] - b[key]) <= 1e-10 * max(abs(a[key]), a["sumsq"] ** 0.5), (key, a[key], b[key])
+
+
+@pytest.mark.parametrize("steps,mode", [(1, "adapted"), (3, "terminal"), (2, "adapted")])
+def test_packed_short_path_kernel_same_law_as_generic_kernel(steps, mode, monkeypatch):
+    """jump_flat1d_kernel (1-D Merton short paths, MLMC level 0) packs the normals, gaps and marks of two iterations
+    into one Philox block: a different stream, the same law.  Against the generic kernel at 2e7 paths each: payoff
+    mean within 4 combined standard errors, second moment and mean iteration count within 4 of theirs; path count
+    exact."""
+    from sde_mc_b200 import _engine as E
+    from sde_mc_b200 import _lib as L
+    from sde_mc_b200 import _spec
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    solver = sm.JumpEulerSolver(sde, 3, steps, device=DEV)
+    payoff = sm.EuroCall(1.0)
+    idx = L.INDEX_TERMINAL if mode == "terminal" else L.INDEX_ADAPTED
+    n = 20_000_001
+    lib = L.load()
+    res = {}
+    for name, flat in (("generic", "0"), ("packed", "1")):
+        monkeypatch.setenv("SDEMC_JUMP_FLAT", flat)
+        with torch.cuda.device(DEV):
+            dev = torch.device(DEV, 0)
+            mom = E.Moments(dev)
+            po = _spec.payoff_struct(payoff, math.exp(-0.06), idx)
+            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(5, 1000, n), L.ptr(mom.buf),
+                                         L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+            res[name] = mom.read()
+    a, b = res["generic"], res["packed"]
+    assert a["n"] == b["n"] == n
+    mean_a, mean_b = a["sum"] / n, b["sum"] / n
+    var_a, var_b = a["sumsq"] / n - mean_a ** 2, b["sumsq"] / n - mean_b ** 2
+    se = math.sqrt((var_a + var_b) / n)
+    assert abs(mean_a - mean_b) < 4 * se, (mean_a, mean_b, se)
+    # second moment: standard error from the fourth moment bound payoff^2 <= 30 * payoff here is loose; use 1 %
+    assert abs(var_a / var_b - 1.0) < 0.01, (var_a, var_b)
+    # iterations per path: Poisson(3)-driven spread, se <= sqrt(3 / n) each
+    it_a, it_b = a["iters"] / n, b["iters"] / n
+    assert abs(it_a - it_b) < 4 * math.sqrt(2 * 3.0 / n) + 1e-4, (it_a, it_b)
+    assert it_b > steps + 1.0                      # every jump before T costs at most one extra iteration
+    if steps == 1:
+        assert abs(it_b - 4.0) < 2e-3              # one nominal step: exactly 1 + Poisson(rate T = 3) iterations
