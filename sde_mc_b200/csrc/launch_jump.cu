@@ -56,9 +56,9 @@ int run_flat(const LaunchArgs& a) {
 }
 
 // 1-D lognormal-mark models: two iterations per Philox block, no alignment across the warp (jump_flat.cuh)
-template <class C>
+template <class C, bool FAST>
 int run_flat1d(const LaunchArgs& a) {
-  auto kernel = jump_flat1d_kernel<C>;
+  auto kernel = jump_flat1d_kernel<C, FAST>;
   int grid = 0;
   int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
   if (rc != SDEMC_OK) return rc;
@@ -85,8 +85,14 @@ int by_mode(const LaunchArgs& a) {
   if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;
   if (a.flat && !a.store && a.qdepth == 0) {
     if constexpr (C::DIM == 1 && C::M == 1 && !C::ASIAN && C::MARKS == SDEMC_MARKS_LOGNORMAL) {
-      const char* e = getenv("SDEMC_JUMP_FLAT_PACKED");  // 0: keep the streams of jump_kernel (aligned groups of six)
-      if (!e || atoi(e) != 0) return run_flat1d<C>(a);
+      // SDEMC_JUMP_FLAT_PACKED = 0: keep the streams of jump_kernel (aligned groups of six); 2: packed stream with
+      // the generic jump_iteration (the form the restated iteration is tested against)
+      const char* e = getenv("SDEMC_JUMP_FLAT_PACKED");
+      const int mode = e ? atoi(e) : 1;
+      if (mode == 1 && !a.sde.milstein && C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
+        if constexpr (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) return run_flat1d<C, true>(a);
+      }
+      if (mode != 0) return run_flat1d<C, false>(a);
     }
     return run_flat<C>(a);
   }

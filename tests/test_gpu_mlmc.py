@@ -221,3 +221,36 @@ def test_packed_short_path_kernel_same_law_as_generic_kernel(steps, mode, monkey
     assert it_b > steps + 1.0                      # every jump before T costs at most one extra iteration
     if steps == 1:
         assert abs(it_b - 4.0) < 2e-3              # one nominal step: exactly 1 + Poisson(rate T = 3) iterations
+
+
+@pytest.mark.parametrize("steps,exact", [(1, False), (1, True), (4, False)])
+def test_packed_kernel_restated_iteration_matches_generic_iteration(steps, exact, monkeypatch):
+    """Same packed stream, two forms of the loop body: the generic jump_iteration (SDEMC_JUMP_FLAT_PACKED=2) and the
+    restated one (stateless mesh, sigma^2 dt folded into the Box-Muller radius, one-FMA hit test; default).  Same
+    draws, same mesh, same hits: iteration totals and all five moment sums equal up to fp32 rounding of the states."""
+    from sde_mc_b200 import _engine as E
+    from sde_mc_b200 import _lib as L
+    from sde_mc_b200 import _spec
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    solver = sm.JumpEulerSolver(sde, 3, steps, device=DEV, exact_jumps=exact)
+    n = 3_000_001
+    lib = L.load()
+    monkeypatch.setenv("SDEMC_JUMP_FLAT", "1")
+    res = {}
+    for mode in ("2", "1"):
+        monkeypatch.setenv("SDEMC_JUMP_FLAT_PACKED", mode)
+        with torch.cuda.device(DEV):
+            dev = torch.device(DEV, 0)
+            mom = E.Moments(dev)
+            po = _spec.payoff_struct(sm.EuroCall(1.0), math.exp(-0.06), L.INDEX_ADAPTED)
+            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(9, 77, n), L.ptr(mom.buf),
+                                         L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+            res[mode] = mom.read()
+    a, b = res["2"], res["1"]
+    assert a["n"] == b["n"] == n
+    # the two hit tests are the same inequality up to the rounding of its right-hand side: a handful of iterations in 1e7
+    assert abs(a["iters"] - b["iters"]) <= 2 + 1e-6 * a["iters"], (a["iters"], b["iters"])
+    # per-path states agree to fp32 rounding (~1e-7, partly systematic): sums within 2e-6 per path; a structural
+    # difference (a different draw, mesh or hit) moves them by >= 1e-3 per path
+    for key in ("sum", "sumsq", "sum_c", "sumsq_c", "sum_pc"):
+        assert abs(a[key] - b[key]) <= 2e-6 * n, (key, a[key], b[key])
