@@ -65,14 +65,14 @@ OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0, "mlmc": 40.0}
 # in profiles/r01_ncu_<workload>.summary.txt (moments kernels touch HBM only for code, parameters and the per-CTA
 # partials; the storing kernels write their trajectories once: 1.006x / 1.067x the algorithmic bytes)
 NCU_DRAM_BYTES_PER_LAUNCH = {"gbm": 43264.0, "merton": 30208.0, "levy2d": 371456.0, "merton_cv": 165120.0,
-                             "gbm_store": 8.128509e9 + 1.26625e8, "merton_store": 5.394213e9 + 3.1638e8, "mlmc": 15104.0}
+                             "gbm_store": 8.128509e9 + 1.26625e8, "merton_store": 5.394213e9 + 3.1638e8, "mlmc": 15616.0}
 # pipe utilisation of the same kernels in those captures (percent of peak while active): issue slots, FMA, ALU, XU and
 # tensor pipes.  The canonical op counts above are larger than what the SASS executes (e.g. GBM 23 vs 14.7
 # instructions per path-step), so `frac` can exceed the issue utilisation; both are reported.
 NCU_PIPE_PCT = {"gbm": dict(issue=65.5, fma=32.0, alu=44.9, xu=72.2), "merton": dict(issue=68.2, fma=30.6, alu=48.1, xu=42.7),
                 "levy2d": dict(issue=66.4, fma=31.9, alu=46.3, xu=47.0),
                 "merton_cv": dict(issue=44.5, fma=5.7, alu=45.5, xu=6.3, tensor=42.4),
-                "mlmc": dict(issue=68.9, fma=27.3, alu=56.4, xu=44.7), "gbm_store": dict(issue=37.3, fma=16.7, alu=24.6, xu=21.6),
+                "mlmc": dict(issue=69.0, fma=26.4, alu=56.2, xu=47.2), "gbm_store": dict(issue=37.3, fma=16.7, alu=24.6, xu=21.6),
                 "merton_store": dict(issue=48.2, fma=15.3, alu=28.0, xu=9.4)}
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 
