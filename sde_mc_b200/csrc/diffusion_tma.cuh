@@ -4,8 +4,9 @@
 // (bs, S+1, dim) and increments (bs, S, dim[, m]), row-per-path), different data path.  The 16-byte-store flush of
 // store_tile.cuh drains through the LSU queue it shares with the staging STS/LDS and does not overlap the step
 // loop (measured: 1.57 ms of compute + 1.2 ms of stores for 8 GB).  Measured here: 2.39 ms
-// against 2.82 ms for the same 8 GB (3.4 TB/s); 1.35 ms with the bulk copy left out, i.e. the limit is now the
-// TMA engine's rate for boxes of 32 separate 128-byte rows.  Here every warp keeps a
+// against 2.82 ms for the same 8 GB (3.4 TB/s); 1.35 ms with the bulk copy left out.  The engine alone moves these
+// boxes at 5.4-5.6 TB/s (tools/tma_box_probe.cu), so copy and step loop hardly overlap yet.
+// Here every warp keeps a
 // [32 paths][32 elements] tile per output array in shared memory in the layout TMA reads (128-byte rows, 128B
 // swizzle), fills it with 16-byte vector stores -- four consecutive elements of a path are collected in registers;
 // lane q writes chunk (v ^ (q & 7)) of row q, conflict free per quarter warp -- and one lane hands the full tile to
