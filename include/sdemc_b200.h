@@ -11,9 +11,13 @@
  *   - plain C, POD structs, no exceptions; every function returns 0 or a negative sdemc_status
  *   - all `d_*` pointers are DEVICE pointers owned by the caller (e.g. torch tensors)
  *   - `stream` is a cudaStream_t (NULL = legacy default stream); calls are asynchronous w.r.t. it
- *   - the library keeps no mutable global state; the caller provides scratch (`d_workspace`)
+ *   - the library keeps no mutable global state and reads no environment variables: every choice of kernel
+ *     is a function of the structs below; the caller provides scratch (`d_workspace`)
  *   - all path arithmetic is fp32 like the reference (torch default dtype); the moment
  *     accumulators are fp64; the MLMC pair entry point also has an fp64-state variant
+ *   - every struct the caller fills starts with `struct_size` = sizeof(that struct): an entry point handed a struct
+ *     of another size (a binding written against another header) returns SDEMC_ERR_BAD_ARG instead of reading past
+ *     it; sdemc_abi_layout() reports the sizes this build expects
  */
 #ifndef SDEMC_B200_H
 #define SDEMC_B200_H
@@ -24,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SDEMC_ABI_VERSION 3
+#define SDEMC_ABI_VERSION 4
 #define SDEMC_MAX_DIM 4
 #define SDEMC_MAX_LEVELS 16
 
@@ -65,6 +69,21 @@ typedef enum { SDEMC_MARKS_NONE = 0, SDEMC_MARKS_LOGNORMAL = 1, SDEMC_MARKS_ICDF
  * dense jumps.  The two strategies consume different Philox counters, so estimates agree statistically only. */
 typedef enum { SDEMC_JUMPS_AUTO = 0, SDEMC_JUMPS_QUEUE = 1, SDEMC_JUMPS_INLINE = 2 } sdemc_jump_strategy;
 
+/* Moments-only kernels for SHORT paths (few nominal steps, several jumps: MLMC level 0), where a warp of the plain
+ * kernel idles until its slowest lane is done.  Lanes become persistent workers (csrc/jump_flat.cuh).
+ *   AUTO    : sdemc_mc_moments picks ALIGNED when 2.1 sqrt(rate T) > 0.2 (num_steps + rate T), else the plain kernel;
+ *             the single-level call of sdemc_mlmc_pair (coarse == 0) picks PACKED under the same rule
+ *   OFF     : always the plain kernel
+ *   ALIGNED : persistent lanes, every path consumes exactly the Philox counters of the plain / path-storing kernels
+ *             (same seed => same paths as sdemc_solve_paths)
+ *   PACKED  : 1-D lognormal-mark models only: normals, gaps and marks of two iterations from ONE Philox block
+ *             (a stream of its own: same law, different paths than sdemc_solve_paths)
+ *   PACKED_GENERIC : PACKED's stream driven through the generic iteration body (what PACKED is tested against) */
+typedef enum {
+  SDEMC_SHORT_AUTO = 0, SDEMC_SHORT_OFF = 1, SDEMC_SHORT_ALIGNED = 2, SDEMC_SHORT_PACKED = 3,
+  SDEMC_SHORT_PACKED_GENERIC = 4
+} sdemc_short_path;
+
 /* options.py:179-321 */
 typedef enum {
   SDEMC_PAYOFF_EURO_CALL = 0, SDEMC_PAYOFF_EURO_PUT = 1, SDEMC_PAYOFF_BINARY_AON = 2,
@@ -79,6 +98,7 @@ typedef enum { SDEMC_INDEX_TERMINAL = 0 /* array index num_steps */, SDEMC_INDEX
 /* The SDE + discretisation, extracted from (Sde, SdeSolver) objects. Replaces the attribute reads in
  * solvers.py:10-37,131-134 and the coefficient callbacks sde.py:63-152. */
 typedef struct {
+  uint32_t struct_size; /* sizeof(sdemc_sde) */
   int32_t family;       /* sdemc_family */
   int32_t scheme;       /* sdemc_scheme */
   int32_t dim;          /* state dimension, 1..SDEMC_MAX_DIM (Sde.dim) */
@@ -89,6 +109,8 @@ typedef struct {
   int32_t exact_jumps;  /* solvers.py:214-217 */
   int32_t asian;        /* 1: AsianWrapper sde.py:378-406 -- component dim-1 integrates component 0 */
   int32_t jump_strategy; /* sdemc_jump_strategy: how Philox jump draws are organised (AUTO picks by rate*T/num_steps) */
+  int32_t queue_depth;  /* QUEUE strategy: pre-drawn jumps per refill, a multiple of 4 in [4, 64]; 0 = sized from rate*T */
+  int32_t short_path;   /* sdemc_short_path */
   float T;              /* SdeSolver.time_interval */
   float x0[SDEMC_MAX_DIM];
   float chol[SDEMC_MAX_DIM * SDEMC_MAX_DIM]; /* lower Cholesky of corr_matrix, row-major, stride SDEMC_MAX_DIM */
@@ -107,6 +129,7 @@ typedef struct {
 
 /* Option + discounter: options.py:156-176 (transform), :179-321 (payoffs), :324-337 (ConstantShortRate) */
 typedef struct {
+  uint32_t struct_size; /* sizeof(sdemc_payoff) */
   int32_t kind;        /* sdemc_payoff_kind */
   int32_t log;         /* Option.log */
   int32_t index_mode;  /* sdemc_index_mode */
@@ -119,6 +142,8 @@ typedef struct {
 /* Which paths, and where their noise comes from.  Philox4x32-10 keyed by `seed`, countered by the GLOBAL
  * path id, so results do not depend on grid shape or on how a range is split over GPUs. */
 typedef struct {
+  uint32_t struct_size; /* sizeof(sdemc_range) */
+  uint32_t reserved;
   uint64_t seed;
   uint64_t path_lo;    /* first global path id of this call */
   uint64_t n_paths;    /* number of paths in this call */
@@ -128,13 +153,15 @@ typedef struct {
  * sample_corr_normals solvers.py:51-56, sample_jump_times :143-144, sample_one_jump :146-148).
  * All arrays are row-major, one row per path. K = number of loop iterations available. */
 typedef struct {
+  uint32_t struct_size;      /* sizeof(sdemc_inject) */
+  int32_t K;
   const float* d_z;          /* (n, K, dim, m') unit normals; m' = m for the diffusion solver, 1 for the jump solver */
   const float* d_zc;         /* (n, K) common unit normal of the 2nd driver (jump solver, m == 2), else NULL */
   const float* d_jump_times; /* (n, max_jumps) cumulative jump times, else NULL */
   const float* d_marks;      /* (n, K) raw mark draw per iteration: N(0,1) for LOGNORMAL, U[0,1) for ICDF */
-  int32_t K;
   int32_t total_steps;       /* sdemc_mc_cv only: the batch's total_steps; the reference's compensator sum drops the
                                 interval with index total_steps-1 (varred.py:104,126-127).  0 = drop nothing. */
+  int32_t reserved;
 } sdemc_inject;
 
 /* fp64 running moments; layout of the device array handed to the kernels (8 doubles). */
@@ -149,12 +176,16 @@ typedef struct {
   double reserved;
 } sdemc_moments;
 
+#define SDEMC_OUT_NO_TMA 1u /* uniform-grid path-storing kernel: 16-byte LSU stores even where the layout allows TMA tiles */
+
 /* Optional trajectory outputs, layouts exactly as the reference allocates them (solvers.py:64-66,150-162).
  * S = num_steps for the diffusion solver, num_steps + max_jumps for the jump solver.  NULL = skip.
  * Rows (one per path) may be padded: pitch_* = floats between consecutive rows, 0 = dense (the reference's
  * contiguous layout).  With a pitch that is a multiple of 4 floats and 16-byte aligned bases the kernels write
  * 16-byte vectors covering whole 128-byte lines; any other pitch takes the 4-byte store path. */
 typedef struct {
+  uint32_t struct_size; /* sizeof(sdemc_paths_out) */
+  uint32_t flags;       /* SDEMC_OUT_* */
   float* d_paths;       /* (n, S+1, dim) */
   float* d_left;        /* (n, S+1, dim)  state before the jump            (jump solver) */
   float* d_times;       /* (n, S+1)       time after each iteration        (jump solver) */
@@ -162,6 +193,7 @@ typedef struct {
   float* d_normals;     /* (n, S, dim[, m]) Brownian increments dW actually used */
   float* d_payoffs;     /* (n)            discounted payoff per path */
   int32_t* d_iters;     /* (n)            executed iterations per path */
+  float* d_terminal;    /* (n, dim)       the state the payoff is applied to (index_mode; ADAPTED without a payoff) */
   int32_t* d_total_steps; /* scalar: max over paths of executed iterations (atomicMax; caller zeroes it) */
   int64_t pitch_state;    /* row pitch of d_paths / d_left / d_jumps, 0 = (S+1)*dim */
   int64_t pitch_times;    /* row pitch of d_times, 0 = S+1 */
@@ -172,6 +204,8 @@ typedef struct {
  * Linear(d+1,H) ReLU Linear(H,H) ReLU Linear(H,H) ReLU Linear(H,out). Weights are torch Linear
  * layouts (out_features, in_features) row-major fp32, device pointers. */
 typedef struct {
+  uint32_t struct_size; /* sizeof(sdemc_mlp) */
+  uint32_t reserved;
   const float* d_w[4];
   const float* d_b[4];
   int32_t in_dim, hidden, out_dim, n_hidden_layers; /* n_hidden_layers == 3 */
@@ -184,12 +218,23 @@ const char* sdemc_last_cuda_error(void);
 int sdemc_device_info(int device, int* sm_count, int* clock_khz, uint64_t* mem_bytes);
 /* Bytes of device scratch every entry point needs (per concurrent call). */
 uint64_t sdemc_workspace_bytes(void);
+/* Layout handshake: writes up to `n` of the sizes {sdemc_sde, sdemc_payoff, sdemc_range, sdemc_inject, sdemc_moments,
+ * sdemc_paths_out, sdemc_mlp} this library was compiled with and returns how many there are (7).  A binding compares
+ * them with its own struct definitions once at load time (sde_mc_b200/_lib.py does). */
+int sdemc_abi_layout(uint32_t* sizes, int n);
 
 /* E1/H3/H10 fused: time-stepping + payoff + (sum, sumsq, ...) reduction; nothing per-path touches HBM.
  * Replaces the bodies of mc_simple mc.py:101-123, mc_terminal_cv mc.py:352-375 and the solve() they call.
- * d_moments (sdemc_moments) is ACCUMULATED into (caller zeroes it once per estimator). */
+ * d_moments (sdemc_moments) is ACCUMULATED into (caller zeroes it once per estimator).
+ * per_path (may be NULL) asks the SAME kernels to also write what each path contributed -- only d_payoffs, d_iters
+ * and d_terminal are honoured, any other output pointer must be NULL (trajectories: sdemc_solve_paths).  This is how
+ * the moments kernels are compared path by path with the path-storing kernel and the oracle. */
 int sdemc_mc_moments(const sdemc_sde* sde, const sdemc_payoff* payoff, const sdemc_range* range,
-                     sdemc_moments* d_moments, void* d_workspace, void* stream);
+                     const sdemc_paths_out* per_path, sdemc_moments* d_moments, void* d_workspace, void* stream);
+
+/* P1-P3: the device payoff function of all kernels (Option.__call__ options.py:167-176 + payoffs :196-321) applied to
+ * n states d_x (n, dim) -> d_out (n), times payoff->df.  index_mode is ignored. */
+int sdemc_eval_payoff(const sdemc_payoff* payoff, int32_t dim, const float* d_x, uint64_t n, float* d_out, void* stream);
 
 /* H3/H10 with storage: the solve() contract (solvers.py:68-88,164-226).  Noise is Philox (inject == NULL)
  * or injected (deterministic parity mode).  Any subset of outputs may be requested. */

@@ -52,9 +52,12 @@ def mean_and_stderr(total, total_sq, n):
     return mean, (var / n) ** 0.5
 
 
-def run_moments(solver, payoff, discounter, num_trials, index_mode, moments=None, num_steps=None, reduce=True):
+def run_moments(solver, payoff, discounter, num_trials, index_mode, moments=None, num_steps=None, reduce=True,
+                per_path=None):
     """Simulate `num_trials` paths (split over the ranks of the default process group) through the fused
-    step-loop + payoff + reduction kernel.  Returns the Moments holder (all-reduced unless reduce=False)."""
+    step-loop + payoff + reduction kernel.  Returns the Moments holder (all-reduced unless reduce=False).
+    per_path: optional dict; filled with this rank's per-path 'payoffs', 'iters' and 'terminal' device tensors
+    (what each path contributed -- the hook the parity tests compare with the path-storing kernel and the oracle)."""
     num_trials = int(num_trials)
     dev = solver._compute_device()
     lib = solver._engine_lib()
@@ -68,8 +71,15 @@ def run_moments(solver, payoff, discounter, num_trials, index_mode, moments=None
         if moments is None:
             moments = Moments(dev)
         rng = L.SdemcRange(int(solver.seed), lo + off, cnt)
-        getattr(lib, 'check', L.check)(lib.sdemc_mc_moments(sde, po, rng, L.ptr(moments.buf), L.ptr(L.workspace(dev)),
-                                                            L.stream_ptr(dev)))
+        pp = None
+        if per_path is not None:
+            per_path['payoffs'] = torch.empty((cnt,), device=dev, dtype=torch.float32)
+            per_path['iters'] = torch.empty((cnt,), device=dev, dtype=torch.int32)
+            per_path['terminal'] = torch.empty((cnt, solver.sde.dim), device=dev, dtype=torch.float32)
+            pp = L.SdemcPathsOut(d_payoffs=L.ptr(per_path['payoffs']), d_iters=L.ptr(per_path['iters']),
+                                 d_terminal=L.ptr(per_path['terminal']))
+        getattr(lib, 'check', L.check)(lib.sdemc_mc_moments(sde, po, rng, pp, L.ptr(moments.buf),
+                                                            L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
         if reduce:
             moments.all_reduce()
     return moments

@@ -16,7 +16,18 @@ from . import _lib as L
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_CACHE = os.environ.get("SDEMC_B200_JIT_DIR", os.path.join(_HERE, "_jit"))
+
+
+def _default_cache():
+    """in the package when it is writable (a source checkout), else the user's cache directory (an installed package)"""
+    local = os.path.join(_HERE, "_jit")
+    if os.access(local if os.path.isdir(local) else _HERE, os.W_OK):
+        return local
+    return os.path.join(os.environ.get("XDG_CACHE_HOME", os.path.join(os.path.expanduser("~"), ".cache")),
+                        "sde_mc_b200", "jit")
+
+
+_CACHE = os.environ.get("SDEMC_B200_JIT_DIR") or _default_cache()
 _loaded = {}
 
 
@@ -66,7 +77,9 @@ def build(dim, marks, code, verbose=False):
     so = os.path.join(_CACHE, "user_%s.so" % key)
     if os.path.exists(so):
         return so
-    cu = os.path.join(_CACHE, "user_%s.cu" % key)
+    # under torchrun every rank builds at once: each writes and compiles its own copy of the source and only the
+    # finished files are renamed into place
+    cu = os.path.join(_CACHE, "user_%s.%d.cu" % (key, os.getpid()))
     with open(cu, "w") as fh:
         fh.write(src)
     tmp = so + ".tmp.%d" % os.getpid()
@@ -74,11 +87,13 @@ def build(dim, marks, code, verbose=False):
            "--expt-relaxed-constexpr", "-shared", "-cudart", "static", "-I", _CSRC, cu, "-o", tmp]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        os.unlink(cu)
         raise L.SdemcError("nvcc failed on the user-defined SDE (check the CUDA expressions in kernel_code()):\n" +
                            res.stderr[-4000:])
     if verbose:
         print(res.stderr)
     os.replace(tmp, so)
+    os.replace(cu, os.path.join(_CACHE, "user_%s.cu" % key))
     return so
 
 
@@ -92,7 +107,7 @@ class UserLibrary:
         lib.sdemc_user_last_cuda_error.restype = C.c_char_p
         lib.sdemc_user_mc_moments.restype = C.c_int
         lib.sdemc_user_mc_moments.argtypes = [C.POINTER(L.SdemcSde), C.POINTER(L.SdemcPayoff), C.POINTER(L.SdemcRange),
-                                              C.c_void_p, C.c_void_p, C.c_void_p]
+                                              C.POINTER(L.SdemcPathsOut), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.sdemc_user_solve_paths.restype = C.c_int
         lib.sdemc_user_solve_paths.argtypes = [C.POINTER(L.SdemcSde), C.POINTER(L.SdemcPayoff), C.POINTER(L.SdemcRange),
                                                C.POINTER(L.SdemcPathsOut), C.c_void_p, C.c_void_p]
@@ -105,8 +120,8 @@ class UserLibrary:
                 msg += " [" + self.lib.sdemc_user_last_cuda_error().decode() + "]"
             raise L.SdemcError("sdemc error %d in the user-model library: %s" % (rc, msg))
 
-    def sdemc_mc_moments(self, sde, po, rng, mom, ws, stream):
-        return self.lib.sdemc_user_mc_moments(sde, po, rng, mom, ws, stream)
+    def sdemc_mc_moments(self, sde, po, rng, per_path, mom, ws, stream):
+        return self.lib.sdemc_user_mc_moments(sde, po, rng, per_path, mom, ws, stream)
 
     def sdemc_solve_paths(self, sde, po, rng, inj, out, ws, stream):
         if inj is not None:

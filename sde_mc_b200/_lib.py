@@ -23,11 +23,24 @@ INDEX_TERMINAL, INDEX_ADAPTED = 0, 1
  PAYOFF_DIGITAL, PAYOFF_ASIAN_CALL, PAYOFF_HESTON_RAINBOW, PAYOFF_BEST_OF) = range(10)
 
 
-class SdemcSde(C.Structure):
+SHORT_AUTO, SHORT_OFF, SHORT_ALIGNED, SHORT_PACKED, SHORT_PACKED_GENERIC = range(5)
+OUT_NO_TMA = 1
+
+
+class _Sized(C.Structure):
+    """Every struct handed to the library starts with struct_size = sizeof(struct) (the ABI's layout handshake);
+    the constructor fills it, positional arguments start at the second field."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(C.sizeof(type(self)), *args, **kw)
+
+
+class SdemcSde(_Sized):
     _fields_ = [
+        ("struct_size", C.c_uint32),
         ("family", C.c_int32), ("scheme", C.c_int32), ("dim", C.c_int32), ("m", C.c_int32), ("marks", C.c_int32),
         ("num_steps", C.c_int32), ("max_jumps", C.c_int32), ("exact_jumps", C.c_int32), ("asian", C.c_int32),
-        ("jump_strategy", C.c_int32),
+        ("jump_strategy", C.c_int32), ("queue_depth", C.c_int32), ("short_path", C.c_int32),
         ("T", C.c_float), ("x0", C.c_float * MAX_DIM), ("chol", C.c_float * (MAX_DIM * MAX_DIM)),
         ("a", C.c_float * MAX_DIM), ("b1", C.c_float * MAX_DIM), ("b2", C.c_float * MAX_DIM),
         ("c", C.c_float * MAX_DIM), ("rate", C.c_float), ("mark_p", C.c_float * 12), ("heston", C.c_float * 4),
@@ -35,30 +48,48 @@ class SdemcSde(C.Structure):
     ]
 
 
-class SdemcPayoff(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("log", C.c_int32), ("index_mode", C.c_int32), ("strike", C.c_float),
-                ("transform_discount", C.c_float), ("aux", C.c_float), ("df", C.c_float)]
+class SdemcPayoff(_Sized):
+    _fields_ = [("struct_size", C.c_uint32), ("kind", C.c_int32), ("log", C.c_int32), ("index_mode", C.c_int32),
+                ("strike", C.c_float), ("transform_discount", C.c_float), ("aux", C.c_float), ("df", C.c_float)]
 
 
-class SdemcRange(C.Structure):
-    _fields_ = [("seed", C.c_uint64), ("path_lo", C.c_uint64), ("n_paths", C.c_uint64)]
+class SdemcRange(_Sized):
+    """SdemcRange(seed, path_lo, n_paths)"""
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("seed", C.c_uint64), ("path_lo", C.c_uint64),
+                ("n_paths", C.c_uint64)]
+
+    def __init__(self, seed=0, path_lo=0, n_paths=0):
+        super().__init__(0, seed, path_lo, n_paths)
 
 
-class SdemcInject(C.Structure):
-    _fields_ = [("d_z", C.c_void_p), ("d_zc", C.c_void_p), ("d_jump_times", C.c_void_p), ("d_marks", C.c_void_p),
-                ("K", C.c_int32), ("total_steps", C.c_int32)]
+class SdemcInject(_Sized):
+    """SdemcInject(d_z, d_zc, d_jump_times, d_marks, K, total_steps=0)"""
+    _fields_ = [("struct_size", C.c_uint32), ("K", C.c_int32), ("d_z", C.c_void_p), ("d_zc", C.c_void_p),
+                ("d_jump_times", C.c_void_p), ("d_marks", C.c_void_p), ("total_steps", C.c_int32),
+                ("reserved", C.c_int32)]
+
+    def __init__(self, d_z=None, d_zc=None, d_jump_times=None, d_marks=None, K=0, total_steps=0):
+        super().__init__(K, d_z, d_zc, d_jump_times, d_marks, total_steps, 0)
 
 
-class SdemcPathsOut(C.Structure):
-    _fields_ = [("d_paths", C.c_void_p), ("d_left", C.c_void_p), ("d_times", C.c_void_p), ("d_jumps", C.c_void_p),
+class SdemcPathsOut(_Sized):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32),
+                ("d_paths", C.c_void_p), ("d_left", C.c_void_p), ("d_times", C.c_void_p), ("d_jumps", C.c_void_p),
                 ("d_normals", C.c_void_p), ("d_payoffs", C.c_void_p), ("d_iters", C.c_void_p),
-                ("d_total_steps", C.c_void_p), ("pitch_state", C.c_int64), ("pitch_times", C.c_int64),
-                ("pitch_normals", C.c_int64)]
+                ("d_terminal", C.c_void_p), ("d_total_steps", C.c_void_p), ("pitch_state", C.c_int64),
+                ("pitch_times", C.c_int64), ("pitch_normals", C.c_int64)]
+
+    def __init__(self, d_paths=None, d_left=None, d_times=None, d_jumps=None, d_normals=None, d_payoffs=None,
+                 d_iters=None, d_total_steps=None, pitch_state=0, pitch_times=0, pitch_normals=0, d_terminal=None,
+                 flags=0):
+        super().__init__(flags, d_paths, d_left, d_times, d_jumps, d_normals, d_payoffs, d_iters, d_terminal,
+                         d_total_steps, pitch_state, pitch_times, pitch_normals)
 
 
-class SdemcMlp(C.Structure):
-    _fields_ = [("d_w", C.c_void_p * 4), ("d_b", C.c_void_p * 4), ("in_dim", C.c_int32), ("hidden", C.c_int32),
-                ("out_dim", C.c_int32), ("n_hidden_layers", C.c_int32)]
+class SdemcMlp(_Sized):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("d_w", C.c_void_p * 4),
+                ("d_b", C.c_void_p * 4), ("in_dim", C.c_int32), ("hidden", C.c_int32), ("out_dim", C.c_int32),
+                ("n_hidden_layers", C.c_int32)]
 
 
 MOMENT_FIELDS = ("sum", "sumsq", "sum_c", "sumsq_c", "sum_pc", "n", "iters", "reserved")
@@ -70,8 +101,10 @@ _SIGNATURES = {
     "sdemc_last_cuda_error": (C.c_char_p, []),
     "sdemc_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
     "sdemc_workspace_bytes": (C.c_uint64, []),
-    "sdemc_mc_moments": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.POINTER(SdemcRange), C.c_void_p,
-                                   C.c_void_p, C.c_void_p]),
+    "sdemc_abi_layout": (C.c_int, [C.POINTER(C.c_uint32), C.c_int]),
+    "sdemc_mc_moments": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.POINTER(SdemcRange),
+                                   C.POINTER(SdemcPathsOut), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdemc_eval_payoff": (C.c_int, [C.POINTER(SdemcPayoff), C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "sdemc_solve_paths": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.POINTER(SdemcRange),
                                     C.POINTER(SdemcInject), C.POINTER(SdemcPathsOut), C.c_void_p, C.c_void_p]),
     "sdemc_mlmc_pair": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.c_int32, C.c_int32, C.c_int32,
@@ -102,11 +135,25 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        if lib.sdemc_version() != ABI_VERSION:
+            raise SdemcError("%s speaks ABI version %d, this binding %d -- rebuild it (make -C sde_mc_b200/csrc)"
+                             % (LIB_PATH, lib.sdemc_version(), ABI_VERSION))
+        theirs = (C.c_uint32 * 7)()
+        lib.sdemc_abi_layout(theirs, 7)
+        if list(theirs) != struct_sizes():
+            raise SdemcError("struct layouts of %s %s differ from this binding's %s" % (LIB_PATH, list(theirs),
+                                                                                      struct_sizes()))
         _lib = lib
     return _lib
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+
+
+def struct_sizes():
+    """sizes in the order of sdemc_abi_layout()"""
+    return [C.sizeof(SdemcSde), C.sizeof(SdemcPayoff), C.sizeof(SdemcRange), C.sizeof(SdemcInject), 8 * NUM_MOMENTS,
+            C.sizeof(SdemcPathsOut), C.sizeof(SdemcMlp)]
 
 
 def load_abi_version():

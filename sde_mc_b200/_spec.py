@@ -71,11 +71,12 @@ def cholesky_rows(corr_matrix, dim):
     return out
 
 
-def sde_struct(spec, T, num_steps, max_jumps=0, exact_jumps=False, jump_strategy=L.JUMPS_AUTO):
+def sde_struct(spec, T, num_steps, max_jumps=0, exact_jumps=False, jump_strategy=L.JUMPS_AUTO, queue_depth=0,
+               short_path=L.SHORT_AUTO):
     s = L.SdemcSde()
     s.family, s.scheme, s.dim, s.m, s.marks = spec.family, spec.scheme, spec.dim, spec.m, spec.marks
     s.num_steps, s.max_jumps, s.exact_jumps, s.asian = int(num_steps), int(max_jumps), int(bool(exact_jumps)), spec.asian
-    s.jump_strategy = int(jump_strategy)
+    s.jump_strategy, s.queue_depth, s.short_path = int(jump_strategy), int(queue_depth), int(short_path)
     s.T = float(T)
     for i in range(L.MAX_DIM):
         s.x0[i], s.a[i], s.b1[i], s.b2[i], s.c[i] = spec.x0[i], spec.a[i], spec.b1[i], spec.b2[i], spec.c[i]

@@ -1,5 +1,5 @@
 // abi.cu -- the extern "C" surface of libsdemc_b200.so (include/sdemc_b200.h)
-#include <mutex>
+#include <algorithm>
 #include <string>
 
 #include "cv.cuh"
@@ -18,6 +18,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 // 0 selects the inline (dense) strategy.
 static int choose_qdepth(const sdemc_sde& s) {
   if (s.marks == SDEMC_MARKS_NONE) return 0;
+  if (s.jump_strategy == SDEMC_JUMPS_QUEUE && s.queue_depth > 0) return s.queue_depth;
   const double lam_T = (double)s.rate * (double)s.T;
   const double per_step = lam_T / (double)s.num_steps;
   int strategy = s.jump_strategy;
@@ -31,10 +32,14 @@ static int choose_qdepth(const sdemc_sde& s) {
 
 static int solve_common(const sdemc_sde* sde, const sdemc_payoff* payoff, const sdemc_range* range,
                         const sdemc_inject* inject, const sdemc_paths_out* out, sdemc_moments* d_moments,
-                        void* d_ws, void* stream, bool store) {
-  if (!valid_sde(sde) || !range) return SDEMC_ERR_BAD_ARG;
+                        void* d_ws, void* stream, bool store, bool prefer_packed = false) {
+  if (!valid_sde(sde) || !sized(range)) return SDEMC_ERR_BAD_ARG;
+  if (!sized_or_null(payoff) || !sized_or_null(inject) || !sized_or_null(out)) return SDEMC_ERR_BAD_ARG;
   if (!store && (!d_moments || !d_ws || !payoff)) return SDEMC_ERR_BAD_ARG;
   if (store && !out) return SDEMC_ERR_BAD_ARG;
+  // moments kernels only report what a path contributed; trajectories are sdemc_solve_paths' business
+  if (!store && out && (out->d_paths || out->d_left || out->d_times || out->d_jumps || out->d_normals || out->d_total_steps))
+    return SDEMC_ERR_BAD_ARG;
   if (range->n_paths == 0) return SDEMC_OK;
   const bool jumps = sde->marks != SDEMC_MARKS_NONE;
   if (inject) {
@@ -56,6 +61,9 @@ static int solve_common(const sdemc_sde* sde, const sdemc_payoff* payoff, const 
   a.d_ws = d_ws;
   a.stream = reinterpret_cast<cudaStream_t>(stream);
   a.qdepth = choose_qdepth(*sde);
+  a.short_path = sde->short_path;
+  a.prefer_packed = prefer_packed;
+  a.no_tma = out && (out->flags & SDEMC_OUT_NO_TMA);
   if (jumps) {
     const int S = inject ? inject->K : sde->num_steps + sde->max_jumps;
     if (!valid_pitches(out, S, sde->dim, sde->dim * sde->m)) return SDEMC_ERR_BAD_ARG;
@@ -67,6 +75,18 @@ static int solve_common(const sdemc_sde* sde, const sdemc_payoff* payoff, const 
   return launch_diffusion(*sde, a);
 }
 
+}  // namespace sdemc
+
+namespace sdemc {
+template <int DIM>
+__global__ void payoff_kernel(const DevPayoff po, const float* __restrict__ x, uint64_t n, float* __restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    float xi[kMaxDim];
+#pragma unroll
+    for (int d = 0; d < kMaxDim; ++d) xi[d] = d < DIM ? x[i * DIM + d] : 0.0f;
+    out[i] = eval_payoff<DIM>(po, xi);
+  }
+}
 }  // namespace sdemc
 
 using namespace sdemc;
@@ -105,9 +125,34 @@ int sdemc_device_info(int device, int* sm_count, int* clock_khz, uint64_t* mem_b
 
 uint64_t sdemc_workspace_bytes(void) { return kWorkspaceBytes; }
 
+int sdemc_abi_layout(uint32_t* sizes, int n) {
+  const uint32_t all[7] = {(uint32_t)sizeof(sdemc_sde),    (uint32_t)sizeof(sdemc_payoff),    (uint32_t)sizeof(sdemc_range),
+                           (uint32_t)sizeof(sdemc_inject), (uint32_t)sizeof(sdemc_moments),   (uint32_t)sizeof(sdemc_paths_out),
+                           (uint32_t)sizeof(sdemc_mlp)};
+  for (int i = 0; sizes && i < n && i < 7; ++i) sizes[i] = all[i];
+  return 7;
+}
+
 int sdemc_mc_moments(const sdemc_sde* sde, const sdemc_payoff* payoff, const sdemc_range* range,
-                     sdemc_moments* d_moments, void* d_workspace, void* stream) {
-  return solve_common(sde, payoff, range, nullptr, nullptr, d_moments, d_workspace, stream, false);
+                     const sdemc_paths_out* per_path, sdemc_moments* d_moments, void* d_workspace, void* stream) {
+  return solve_common(sde, payoff, range, nullptr, per_path, d_moments, d_workspace, stream, false);
+}
+
+
+int sdemc_eval_payoff(const sdemc_payoff* payoff, int32_t dim, const float* d_x, uint64_t n, float* d_out, void* stream) {
+  if (!sized(payoff) || dim < 1 || dim > SDEMC_MAX_DIM || (n > 0 && (!d_x || !d_out))) return SDEMC_ERR_BAD_ARG;
+  if (n == 0) return SDEMC_OK;
+  const DevPayoff po = to_dev(payoff);
+  const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dim) {
+    case 1: payoff_kernel<1><<<grid, 256, 0, st>>>(po, d_x, n, d_out); break;
+    case 2: payoff_kernel<2><<<grid, 256, 0, st>>>(po, d_x, n, d_out); break;
+    case 3: payoff_kernel<3><<<grid, 256, 0, st>>>(po, d_x, n, d_out); break;
+    default: payoff_kernel<4><<<grid, 256, 0, st>>>(po, d_x, n, d_out); break;
+  }
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
 }
 
 int sdemc_solve_paths(const sdemc_sde* sde, const sdemc_payoff* payoff, const sdemc_range* range,
@@ -122,7 +167,8 @@ extern "C" {
 int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse, int32_t use_fp64,
                     const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments, void* d_pair_out,
                     void* d_workspace, void* stream) {
-  if (!valid_sde(sde) || !range || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
+  if (!valid_sde(sde) || !sized(range) || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
+  if (!sized_or_null(payoff) || !sized_or_null(inject)) return SDEMC_ERR_BAD_ARG;
   if (fine < 1 || coarse < 0) return SDEMC_ERR_BAD_ARG;
   if (use_fp64) return SDEMC_ERR_UNSUPPORTED;  // fp64 path state: not built (the fp32 pair clamps dt instead of asserting)
   if (coarse == 0) {
@@ -132,7 +178,7 @@ int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fi
     lvl.num_steps = fine;
     sdemc_payoff po = *payoff;
     po.index_mode = SDEMC_INDEX_ADAPTED;
-    return solve_common(&lvl, &po, range, nullptr, nullptr, d_moments, d_workspace, stream, false);
+    return solve_common(&lvl, &po, range, nullptr, nullptr, d_moments, d_workspace, stream, false, /*prefer_packed=*/true);
   }
   if (fine % coarse != 0 || fine == coarse) return SDEMC_ERR_BAD_ARG;
   if (range->n_paths == 0) return SDEMC_OK;
@@ -153,6 +199,7 @@ int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fi
   a.use_inject = inject != nullptr;
   a.store = false;
   a.qdepth = 0;
+  a.short_path = sde->short_path;
   a.d_moments = reinterpret_cast<double*>(d_moments);
   a.d_ws = d_workspace;
   a.stream = reinterpret_cast<cudaStream_t>(stream);
@@ -161,7 +208,7 @@ int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fi
 }
 
 static bool mlp_ok(const sdemc_mlp* m) {
-  if (!m) return false;
+  if (!sized(m)) return false;
   for (int i = 0; i < 4; ++i)
     if (!m->d_w[i] || !m->d_b[i]) return false;
   return m->in_dim == 2 && m->out_dim == 1 && m->n_hidden_layers == 3 && m->hidden >= 1 && m->hidden <= 63;
@@ -179,7 +226,8 @@ static DevMlp mlp_dev(const sdemc_mlp* m) {
 int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rate, float jump_mean, const sdemc_mlp* f,
                 const sdemc_mlp* g, const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments,
                 float* d_gamma_out, void* d_workspace, void* stream) {
-  if (!valid_sde(sde) || !payoff || !range || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
+  if (!valid_sde(sde) || !sized(payoff) || !sized(range) || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
+  if (!sized_or_null(inject) || !sized_or_null(f) || !sized_or_null(g)) return SDEMC_ERR_BAD_ARG;
   const bool jumps = sde->marks != SDEMC_MARKS_NONE;
   if (!mlp_ok(f) || (jumps && !mlp_ok(g))) return SDEMC_ERR_UNSUPPORTED;
   if (range->n_paths == 0) return SDEMC_OK;

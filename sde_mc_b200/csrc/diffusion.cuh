@@ -189,8 +189,13 @@ __global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, S
       wnorm.flush();
       if (valid && out.payoffs) out.payoffs[i] = pay;
       if (valid && out.iters) out.iters[i] = S;
+      if (valid && out.terminal) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) out.terminal[i * DIM + d] = x[d];
+      }
     } else {
       acc.add(pay, po.df * x[0] - s.x0[0], S);  // terminal control  D(T) x_T[0] - x_0[0]  mc.py:337
+      write_per_path<DIM>(per_path_of_out(out), i, pay, S, x);
     }
   }
   if (!STORE) block_reduce_and_publish(acc, d_moments, d_ws);

@@ -222,6 +222,10 @@ __global__ void __launch_bounds__(kTmaStoreBlock)
     const float pay = eval_payoff<DIM>(po, x);
     if (valid && out.payoffs) out.payoffs[i] = pay;
     if (valid && out.iters) out.iters[i] = S;
+    if (valid && out.terminal) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) out.terminal[i * DIM + d] = x[d];
+    }
   }
   // all bulk stores of this thread complete before the CTA retires
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

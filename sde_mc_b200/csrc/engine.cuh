@@ -65,10 +65,37 @@ struct DevOut {
   float* normals;
   float* payoffs;
   int* iters;
+  float* terminal;  // (n, dim) state the payoff is applied to
   int* total_steps;
   int S;  // allocated iterations per path (rows are S+1 / S long)
   uint64_t pitch_state, pitch_times, pitch_normals;  // floats between consecutive path rows
 };
+
+// per-path outputs of the MOMENTS kernels (sdemc_mc_moments per_path): what every path contributed, so the fast
+// kernels can be compared path by path with the path-storing kernel and the oracle.  All NULL in production runs.
+struct DevPerPath {
+  float* payoffs;
+  int* iters;
+  float* terminal;
+  __device__ __forceinline__ bool any() const { return payoffs != nullptr || iters != nullptr || terminal != nullptr; }
+};
+template <int DIM, class X>
+__device__ __forceinline__ void write_per_path(const DevPerPath& pp, uint64_t i, float pay, int iters, const X& xp) {
+  if (pp.payoffs) pp.payoffs[i] = pay;
+  if (pp.iters) pp.iters[i] = iters;
+  if (pp.terminal) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) pp.terminal[i * DIM + d] = xp[d];
+  }
+}
+
+__host__ __device__ __forceinline__ DevPerPath per_path_of_out(const DevOut& o) {
+  DevPerPath pp;
+  pp.payoffs = o.payoffs;
+  pp.iters = o.iters;
+  pp.terminal = o.terminal;
+  return pp;
+}
 
 // compile-time configuration of a kernel instance
 template <int FAMILY_, int DIM_, int M_, int MARKS_, bool ASIAN_>

@@ -23,8 +23,14 @@ void set_cuda_error(cudaError_t e, const char* where);
     }                                                \
   } while (0)
 
+// struct_size handshake (include/sdemc_b200.h): a struct laid out by another header is rejected, not read
+template <class T>
+inline bool sized(const T* p) { return p != nullptr && p->struct_size == (uint32_t)sizeof(T); }
+template <class T>
+inline bool sized_or_null(const T* p) { return p == nullptr || p->struct_size == (uint32_t)sizeof(T); }
+
 inline bool valid_sde(const sdemc_sde* s) {
-  if (!s) return false;
+  if (!sized(s)) return false;
   if (s->dim < 1 || s->dim > SDEMC_MAX_DIM) return false;
   if (s->m < 1 || s->m > 2) return false;
   if (s->num_steps < 1) return false;
@@ -32,6 +38,8 @@ inline bool valid_sde(const sdemc_sde* s) {
   if (s->marks != SDEMC_MARKS_NONE && !(s->rate > 0.0f)) return false;
   if (s->asian && s->dim < 2) return false;
   if (s->scheme == SDEMC_SCHEME_MILSTEIN && (s->m != 1 || s->family == SDEMC_FAMILY_HESTON)) return false;
+  if (s->queue_depth < 0 || s->queue_depth > 64 || (s->queue_depth & 3)) return false;
+  if (s->short_path < SDEMC_SHORT_AUTO || s->short_path > SDEMC_SHORT_PACKED_GENERIC) return false;
   return true;
 }
 
@@ -121,7 +129,7 @@ inline DevOut to_dev(const sdemc_paths_out* o, int S, int dim = 1, int normals_p
   d.pitch_normals = (uint64_t)S * normals_per_step;
   if (o) {
     d.paths = o->d_paths; d.left = o->d_left; d.times = o->d_times; d.jumps = o->d_jumps;
-    d.normals = o->d_normals; d.payoffs = o->d_payoffs; d.iters = o->d_iters; d.total_steps = o->d_total_steps;
+    d.normals = o->d_normals; d.payoffs = o->d_payoffs; d.iters = o->d_iters; d.terminal = o->d_terminal; d.total_steps = o->d_total_steps;
     if (o->pitch_state > 0) d.pitch_state = (uint64_t)o->pitch_state;
     if (o->pitch_times > 0) d.pitch_times = (uint64_t)o->pitch_times;
     if (o->pitch_normals > 0) d.pitch_normals = (uint64_t)o->pitch_normals;

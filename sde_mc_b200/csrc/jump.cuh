@@ -492,8 +492,13 @@ __global__ void __launch_bounds__(256, jump_min_blocks<C, JSRC, STORE>()) jump_k
       if (valid && out.payoffs) out.payoffs[i] = pay;
       if (valid && out.iters) out.iters[i] = own_iters;
       if (valid) local_max_iters = max(local_max_iters, own_iters);
+      if (valid && out.terminal) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) out.terminal[i * DIM + d] = xp[d];
+      }
     } else {
       acc.add(pay, po.df * st.x[0] - s.x0[0], own_iters);
+      write_per_path<DIM>(per_path_of_out(out), i, pay, own_iters, xp);
     }
   }
   if (STORE) {

@@ -28,7 +28,7 @@ constexpr int kQueueSlack = kNormalsPerBlock;  // slots a speculative group may 
 template <class C, bool EXACT>
 __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
     jump1d_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys, const int qdepth,
-                  double* __restrict__ d_moments, void* __restrict__ d_ws) {
+                  const DevPerPath pp, double* __restrict__ d_moments, void* __restrict__ d_ws) {
   static_assert(C::DIM == 1 && C::M == 1 && !C::ASIAN, "1-D single-driver models only");
   constexpr int MARKS = C::MARKS;
   constexpr int G = kNormalsPerBlock;  // iterations per group
@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
     for (int d = 0; d < kMaxDim; ++d) xp[d] = 0.0f;
     xp[0] = po.index_mode == SDEMC_INDEX_TERMINAL ? x_at_n : x;
     const float pay = eval_payoff<1>(po, xp);
+    write_per_path<1>(pp, i, pay, k, xp);
     {
       Accum one;  // this path's contribution, folded into the thread's shared column
       one.zero();

@@ -19,7 +19,7 @@ namespace sdemc {
 template <class C>
 __global__ void __launch_bounds__(256, 3)
     jump_flat_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys,
-                     double* __restrict__ d_moments, void* __restrict__ d_ws) {
+                     const DevPerPath pp, double* __restrict__ d_moments, void* __restrict__ d_ws) {
   constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M, MARKS = C::MARKS;
   constexpr int NZ = BASE + (M == 2 ? 1 : 0);  // normals per iteration
   constexpr int SPB = steps_per_group(NZ);     // iterations served by one group of Philox blocks
@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256, 3)
       // a path that stopped before array index num_steps idles there with dt = 0: index num_steps holds the final state
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) xp[d] = (po.index_mode == SDEMC_INDEX_TERMINAL && st.k >= n) ? xs[d] : st.x[d];
-      acc.add(eval_payoff<DIM>(po, xp), po.df * st.x[0] - s.x0[0], st.k);
+      const float pay = eval_payoff<DIM>(po, xp);
+      acc.add(pay, po.df * st.x[0] - s.x0[0], st.k);
+      write_per_path<DIM>(pp, i, pay, st.k, xp);
       i += stride;
       live = i < rg.n_paths;
       if (live) start_path(i);
@@ -128,7 +130,7 @@ struct PackedJumps {
 template <class C, bool FAST>
 __global__ void __launch_bounds__(256, 3)
     jump_flat1d_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys,
-                       double* __restrict__ d_moments, void* __restrict__ d_ws) {
+                       const DevPerPath pp, double* __restrict__ d_moments, void* __restrict__ d_ws) {
   static_assert(C::DIM == 1 && C::M == 1 && !C::ASIAN && C::MARKS == SDEMC_MARKS_LOGNORMAL, "1-D lognormal-mark models");
   static_assert(!FAST || C::FAMILY == SDEMC_FAMILY_GEOMETRIC, "the restated iteration is the geometric Euler step");
   using Src = PackedJumps<C::MARKS>;
@@ -209,7 +211,9 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll
       for (int d = 0; d < kMaxDim; ++d) xp[d] = 0.0f;
       xp[0] = (po.index_mode == SDEMC_INDEX_TERMINAL && st.k >= n) ? x_at_n : st.x[0];
-      acc.add(eval_payoff<1>(po, xp), po.df * st.x[0] - s.x0[0], st.k);
+      const float pay = eval_payoff<1>(po, xp);
+      acc.add(pay, po.df * st.x[0] - s.x0[0], st.k);
+      write_per_path<1>(pp, i, pay, st.k, xp);
       i += stride;
       live = i < rg.n_paths;
       if (live) start_path(i);

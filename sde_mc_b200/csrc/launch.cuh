@@ -14,7 +14,9 @@ struct LaunchArgs {
   bool use_inject;
   bool store;
   int qdepth;          // jump queue depth (multiple of 4), 0 => inline jump strategy
-  bool flat = false;   // short paths: persistent-lane kernel (set by launch_jump)
+  int short_path = SDEMC_SHORT_AUTO;  // sdemc_short_path as resolved by the entry point (AUTO: see launch_jump.cu)
+  bool prefer_packed = false;         // AUTO resolves to PACKED instead of ALIGNED (single-level call of sdemc_mlmc_pair)
+  bool no_tma = false;                // path-storing: SDEMC_OUT_NO_TMA
   double* d_moments;
   void* d_ws;
   cudaStream_t stream;

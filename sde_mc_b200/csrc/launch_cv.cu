@@ -1,5 +1,4 @@
 // launch_cv.cu -- instantiation + dispatch of the fused control-variate kernel (cv.cuh)
-#include <cstdlib>
 #include <type_traits>
 
 #include "cv.cuh"
@@ -18,7 +17,6 @@ int run(Kernel kernel, const LaunchArgs& a, const DevMlp& f, const DevMlp& g, co
   // two CTAs per SM: 2 x ~105 KB of shared memory, 2 x 256 of the SM's 512 TMEM columns
   // (the occupancy API under-reports co-residency of large-shared-memory CTAs here; measured)
   per_sm = (227 * 1024) / (kCvSmemBytes + 4096);
-  if (const char* e = getenv("SDEMC_CV_CTAS_PER_SM")) per_sm = atoi(e);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 512 / kCvTmemCols) per_sm = 512 / kCvTmemCols;
   uint64_t grid = (uint64_t)sms * per_sm;

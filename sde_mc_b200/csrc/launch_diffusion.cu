@@ -1,6 +1,4 @@
 // launch_diffusion.cu -- instantiation + dispatch of the uniform-grid kernels (diffusion.cuh)
-#include <cstdlib>
-
 #include <cudaTypedefs.h>
 
 #include "diffusion.cuh"
@@ -47,7 +45,7 @@ int run_store_tma(const LaunchArgs& a) {
   constexpr int NPS = C::BASE * C::M + (C::ASIAN ? 1 : 0);
   if (!tma_rows_ok(a.out.paths, a.out.pitch_state) || !tma_rows_ok(a.out.normals, a.out.pitch_normals)) return 1;
   if (a.range.n_paths >= (1ull << 31)) return 1;
-  if (getenv("SDEMC_NO_TMA_STORE")) return 1;
+  if (a.no_tma) return 1;
   CUtensorMap mp, mn;
   const uint64_t S = (uint64_t)a.sde.num_steps;
   if (!make_row_map(&mp, a.out.paths, a.range.n_paths, (S + 1) * C::DIM, a.out.pitch_state)) return 1;

@@ -2,7 +2,6 @@
 #include <type_traits>
 
 #include <cmath>
-#include <cstdlib>
 
 #include "jump1d.cuh"
 #include "jump_flat.cuh"
@@ -38,7 +37,8 @@ int run_1d(const LaunchArgs& a) {
   int grid = 0;
   int rc = pick_grid(kernel, smem, a.range.n_paths, &grid);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.qdepth, a.d_moments, a.d_ws);
+  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.qdepth, per_path_of_out(a.out),
+                                           a.d_moments, a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
 }
@@ -50,7 +50,7 @@ int run_flat(const LaunchArgs& a) {
   int grid = 0;
   int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.d_moments, a.d_ws);
+  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, per_path_of_out(a.out), a.d_moments, a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
 }
@@ -62,16 +62,15 @@ int run_flat1d(const LaunchArgs& a) {
   int grid = 0;
   int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.d_moments, a.d_ws);
+  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, per_path_of_out(a.out), a.d_moments, a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
 }
 
 // A warp of jump_kernel runs until its slowest lane is done: E[max of 32 Poisson(rate T)] exceeds the mean by about
 // 2.1 sqrt(rate T) iterations.  When that is more than a fifth of a path's num_steps + rate T iterations the
-// persistent-lane kernel wins (MLMC level 0: 2.1 * 1.7 / 4).  SDEMC_JUMP_FLAT=0/1 overrides (benchmarks).
+// persistent-lane kernel wins (MLMC level 0: 2.1 * 1.7 / 4).  sdemc_sde.short_path overrides the rule.
 bool want_flat(const sdemc_sde& s) {
-  if (const char* e = getenv("SDEMC_JUMP_FLAT")) return atoi(e) != 0;
   const double lam_T = (double)s.rate * (double)s.T;
   return 2.1 * std::sqrt(lam_T) > 0.2 * ((double)s.num_steps + lam_T);
 }
@@ -83,18 +82,16 @@ int by_mode(const LaunchArgs& a) {
       return a.sde.exact_jumps ? run_1d<C, true>(a) : run_1d<C, false>(a);
   }
   if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;
-  if (a.flat && !a.store && a.qdepth == 0) {
+  if (a.short_path != SDEMC_SHORT_OFF && !a.store && a.qdepth == 0) {
+    if (a.short_path == SDEMC_SHORT_ALIGNED) return run_flat<C>(a);
+    // PACKED / PACKED_GENERIC: the stream of its own, 1-D lognormal-mark models only
     if constexpr (C::DIM == 1 && C::M == 1 && !C::ASIAN && C::MARKS == SDEMC_MARKS_LOGNORMAL) {
-      // SDEMC_JUMP_FLAT_PACKED = 0: keep the streams of jump_kernel (aligned groups of six); 2: packed stream with
-      // the generic jump_iteration (the form the restated iteration is tested against)
-      const char* e = getenv("SDEMC_JUMP_FLAT_PACKED");
-      const int mode = e ? atoi(e) : 1;
-      if (mode == 1 && !a.sde.milstein && C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
-        if constexpr (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) return run_flat1d<C, true>(a);
+      if constexpr (C::FAMILY == SDEMC_FAMILY_GEOMETRIC) {
+        if (a.short_path == SDEMC_SHORT_PACKED && !a.sde.milstein) return run_flat1d<C, true>(a);
       }
-      if (mode != 0) return run_flat1d<C, false>(a);
+      return run_flat1d<C, false>(a);
     }
-    return run_flat<C>(a);
+    return SDEMC_ERR_UNSUPPORTED;
   }
   if (a.qdepth > 0) return a.store ? run<C, JSRC_QUEUE, true>(a) : run<C, JSRC_QUEUE, false>(a);
   return a.store ? run<C, JSRC_INLINE, true>(a) : run<C, JSRC_INLINE, false>(a);
@@ -115,8 +112,14 @@ int by_dim(const sdemc_sde& s, const LaunchArgs& a) {
 
 int launch_jump(const sdemc_sde& s, const LaunchArgs& a_in) {
   LaunchArgs a = a_in;
-  a.flat = want_flat(s);
   if (a.qdepth < 0 || (a.qdepth & 3) || a.qdepth > 64) return SDEMC_ERR_BAD_ARG;
+  // resolve AUTO.  mc_moments keeps the Philox streams of the path-storing kernels (ALIGNED), so the batched and the
+  // one-shot estimators of one seed agree; the MLMC single-level call takes the packed stream where it exists.
+  if (a.short_path == SDEMC_SHORT_AUTO) {
+    const bool packable = s.dim == 1 && s.m == 1 && !s.asian && s.marks == SDEMC_MARKS_LOGNORMAL;
+    a.short_path = !want_flat(s) ? SDEMC_SHORT_OFF
+                                 : ((a.prefer_packed && packable) ? SDEMC_SHORT_PACKED : SDEMC_SHORT_ALIGNED);
+  }
   if (s.asian) {
     if (s.dim == 2 && s.m == 1 && s.family == SDEMC_FAMILY_GEOMETRIC && s.marks == SDEMC_MARKS_LOGNORMAL)
       return by_mode<Cfg<SDEMC_FAMILY_GEOMETRIC, 2, 1, SDEMC_MARKS_LOGNORMAL, true>>(a);

@@ -1,6 +1,5 @@
 // launch_pair.cu -- instantiation + dispatch of the MLMC pair kernels (pair.cuh)
 #include <cmath>
-#include <cstdlib>
 #include <type_traits>
 
 #include "launch.cuh"
@@ -23,9 +22,9 @@ int run(Kernel kernel, const LaunchArgs& a, int fine, int coarse, float* d_termi
 }
 
 // moments-only pairs with persistent lanes (pair.cuh): same rule as launch_jump.cu:want_flat with the pair's
-// coarse + rate T outer iterations.  SDEMC_PAIR_FLAT=0/1 overrides (benchmarks).
-bool want_flat_pair(const DevSde& s, int coarse) {
-  if (const char* e = getenv("SDEMC_PAIR_FLAT")) return atoi(e) != 0;
+// coarse + rate T outer iterations.  sdemc_sde.short_path overrides (OFF: never, anything else but AUTO: always).
+bool want_flat_pair(const DevSde& s, int coarse, int short_path) {
+  if (short_path != SDEMC_SHORT_AUTO) return short_path != SDEMC_SHORT_OFF;
   const double lam_T = (double)s.rate * (double)s.T;
   return 2.1 * std::sqrt(lam_T) > 0.2 * ((double)coarse + lam_T);
 }
@@ -43,7 +42,7 @@ int run_flat(const LaunchArgs& a, int fine, int coarse) {
 
 template <class C>
 int jump_by_mode(const LaunchArgs& a, int fine, int coarse, float* t) {
-  if (!a.use_inject && t == nullptr && want_flat_pair(a.sde, coarse)) return run_flat<C>(a, fine, coarse);
+  if (!a.use_inject && t == nullptr && want_flat_pair(a.sde, coarse, a.short_path)) return run_flat<C>(a, fine, coarse);
   return a.use_inject ? run(jump_pair_kernel<C, true>, a, fine, coarse, t) : run(jump_pair_kernel<C, false>, a, fine, coarse, t);
 }
 template <class C>

@@ -58,7 +58,10 @@ class SdeSolver(ABC):
             self.lower_cholesky = torch.tensor([[1.]], device=device)
         torch.manual_seed(seed)       # the reference reseeds torch's global RNG here (solvers.py:37)
         self._next_path = 0           # global Philox path id of the next path to simulate
-        self.jump_strategy = L.JUMPS_AUTO
+        self.jump_strategy = L.JUMPS_AUTO    # sdemc_jump_strategy: how the kernels draw compound-Poisson jumps
+        self.queue_depth = 0                 # QUEUE strategy: pre-drawn jumps per refill (0 = sized from rate * T)
+        self.short_path = L.SHORT_AUTO       # sdemc_short_path: persistent-lane kernels for short paths
+        self.tma_store = True                # uniform-grid solve(): TMA tiles where the layout allows them
         # Row pitch of stored trajectories in floats: rows are padded to a multiple of this (32 floats = one
         # 128-byte line) so the path-storing kernels can use 16-byte vector stores.  Set to 1 for the reference's
         # dense (contiguous) allocations -- same values, 4-byte store path.
@@ -92,7 +95,8 @@ class SdeSolver(ABC):
             import dataclasses
             spec = dataclasses.replace(spec, scheme=L.SCHEME_MILSTEIN)
         return _spec.sde_struct(spec, self.time_interval, self.num_steps if num_steps is None else num_steps,
-                                self._max_jumps(), self._exact_jumps(), self.jump_strategy)
+                                self._max_jumps(), self._exact_jumps(), self.jump_strategy, self.queue_depth,
+                                self.short_path)
 
     def _engine_lib(self):
         """the library serving this solver's model: the stock engine or the JIT-built one of a user-defined SDE"""
@@ -146,7 +150,7 @@ class DiffusionSolver(SdeSolver):
             normals, p_norm = _alloc_rows(bs, (S, d) if m == 1 else (S, d, m), dev, self.row_align)
             payoffs = torch.empty((bs,), device=dev, dtype=torch.float32) if want_payoff is not None else None
             out = L.SdemcPathsOut(L.ptr(paths), None, None, None, L.ptr(normals), L.ptr(payoffs), None, None,
-                                  p_state, 0, p_norm)
+                                  p_state, 0, p_norm, flags=0 if self.tma_store else L.OUT_NO_TMA)
             inj = None
             keep = []
             if inject is not None:

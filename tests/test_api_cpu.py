@@ -211,31 +211,109 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sdemc_version() == 3
+    assert lib.sdemc_version() == L.ABI_VERSION == 4
     assert lib.sdemc_workspace_bytes() >= 64 + 8 * 8
     assert b"bad argument" in lib.sdemc_strerror(-1) and lib.sdemc_strerror(0) == b"ok"
 
 
+_C_NAMES = {"SdemcSde": "sdemc_sde", "SdemcPayoff": "sdemc_payoff", "SdemcRange": "sdemc_range",
+            "SdemcInject": "sdemc_inject", "SdemcPathsOut": "sdemc_paths_out", "SdemcMlp": "sdemc_mlp"}
+
+
 def test_struct_layouts_match_the_header():
-    src = '#include <stdio.h>\n#include "sdemc_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
-          'sizeof(sdemc_sde),sizeof(sdemc_payoff),sizeof(sdemc_range),sizeof(sdemc_inject),sizeof(sdemc_moments),' \
-          'sizeof(sdemc_paths_out),sizeof(sdemc_mlp));return 0;}'
+    """A C program that includes include/sdemc_b200.h prints sizeof of every struct and offsetof of every field; both
+    must equal what the ctypes mirror in _lib.py lays out, and what the built library reports (sdemc_abi_layout)."""
+    classes = [getattr(L, n) for n in _C_NAMES]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sdemc_b200.h"', 'int main(){']
+    for cls in classes:
+        c = _C_NAMES[cls.__name__]
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (c, c))
+        for name, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (c, name, c, name))
+    lines.append('printf("sdemc_moments %zu\\n", sizeof(sdemc_moments));')
+    lines.append('printf("version %d\\n", SDEMC_ABI_VERSION); return 0;}')
     with tempfile.TemporaryDirectory() as d:
-        open(os.path.join(d, "s.c"), "w").write(src)
-        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")],
-                       check=True)
-        sizes = [int(v) for v in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True).stdout.split()]
-    ours = [ctypes.sizeof(c) for c in (L.SdemcSde, L.SdemcPayoff, L.SdemcRange, L.SdemcInject)] + \
-           [8 * L.NUM_MOMENTS, ctypes.sizeof(L.SdemcPathsOut), ctypes.sizeof(L.SdemcMlp)]
-    assert sizes == ours
+        open(os.path.join(d, "s.c"), "w").write("\n".join(lines))
+        subprocess.run(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"),
+                        os.path.join(d, "s.c")], check=True)
+        out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout
+    theirs = dict((ln.split()[0], int(ln.split()[1])) for ln in out.splitlines())
+    for cls in classes:
+        c = _C_NAMES[cls.__name__]
+        assert theirs[c] == ctypes.sizeof(cls), c
+        for name, _ in cls._fields_:
+            assert theirs["%s.%s" % (c, name)] == getattr(cls, name).offset, (c, name)
+        assert cls().struct_size == ctypes.sizeof(cls)        # the constructor fills the handshake field
+    assert theirs["sdemc_moments"] == 8 * L.NUM_MOMENTS
+    assert theirs["version"] == L.ABI_VERSION
+    lib = L.load()
+    sizes = (ctypes.c_uint32 * 7)()
+    assert lib.sdemc_abi_layout(sizes, 7) == 7
+    assert list(sizes) == L.struct_sizes() == [theirs[c] for c in ("sdemc_sde", "sdemc_payoff", "sdemc_range",
+                                                                    "sdemc_inject", "sdemc_moments",
+                                                                    "sdemc_paths_out", "sdemc_mlp")]
+
+
+def test_integration_md_binding_snippet_lays_out_the_same_structs():
+    """INTEGRATION.md shows the ctypes classes a maintainer of the reference would paste; they must be the header's."""
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes as C, torch\n.*?)```", text, re.S).group(1)
+    ns = {}
+    code = block.split("# ---- call site")[0].replace('C.CDLL("libsdemc_b200.so")', 'C.CDLL(%r)' % L.LIB_PATH)
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    ns["_check_layout"]()                                   # the snippet's own handshake against the built library
+    for name in ("SdemcSde", "SdemcRange", "SdemcPathsOut"):
+        assert ctypes.sizeof(ns[name]) == ctypes.sizeof(getattr(L, name)), name
+        assert [f[0] for f in ns[name]._fields_] == [f[0] for f in getattr(L, name)._fields_], name
 
 
 def test_bad_arguments_are_rejected_without_touching_a_gpu():
     lib = L.load()
-    assert lib.sdemc_mc_moments(None, None, None, None, None, None) == -1
+    assert lib.sdemc_mc_moments(None, None, None, None, None, None, None) == -1
     s = L.SdemcSde()
     s.dim, s.m, s.num_steps, s.T = 9, 1, 10, 1.0
     assert lib.sdemc_solve_paths(s, None, L.SdemcRange(1, 0, 4), None, L.SdemcPathsOut(), None, None) == -1
+
+
+def test_struct_size_handshake_rejects_foreign_layouts():
+    """a struct laid out by another header version (wrong struct_size) is refused with BAD_ARG, never read past"""
+    lib = L.load()
+    good = sm._spec.sde_struct(sm.Gbm(0.02, 0.3, torch.tensor([1.0]), 1).kernel_spec(), 3.0, 10)
+    po = sm._spec.payoff_struct(sm.EuroCall(1.0), 1.0, L.INDEX_ADAPTED)
+    fake = ctypes.c_void_p(16)       # non-NULL placeholders: validation happens before any dereference on the device
+    rng = L.SdemcRange(1, 0, 0)      # zero paths: a fully valid call returns OK without touching a GPU
+    assert lib.sdemc_mc_moments(good, po, rng, None, fake, fake, None) == 0
+    short = sm._spec.sde_struct(sm.Gbm(0.02, 0.3, torch.tensor([1.0]), 1).kernel_spec(), 3.0, 10)
+    short.struct_size = 256          # the layout INTEGRATION.md showed in round 1
+    assert lib.sdemc_mc_moments(short, po, rng, None, fake, fake, None) == -1
+    bad_po = sm._spec.payoff_struct(sm.EuroCall(1.0), 1.0, L.INDEX_ADAPTED)
+    bad_po.struct_size = 28
+    assert lib.sdemc_mc_moments(good, bad_po, rng, None, fake, fake, None) == -1
+    bad_rng = L.SdemcRange(1, 0, 0)
+    bad_rng.struct_size = 24
+    assert lib.sdemc_mc_moments(good, po, bad_rng, None, fake, fake, None) == -1
+    out = L.SdemcPathsOut()
+    out.struct_size = 88
+    assert lib.sdemc_solve_paths(good, po, rng, None, out, fake, None) == -1
+    # trajectories are not a per-path output of the moments kernels
+    traj = L.SdemcPathsOut(d_paths=fake)
+    assert lib.sdemc_mc_moments(good, po, rng, traj, fake, fake, None) == -1
+    assert lib.sdemc_eval_payoff(bad_po, 1, fake, 4, fake, None) == -1
+    # kernel choices are struct fields, validated like the rest
+    good.queue_depth = 6
+    assert lib.sdemc_mc_moments(good, po, rng, None, fake, fake, None) == -1
+    good.queue_depth, good.short_path = 0, 9
+    assert lib.sdemc_mc_moments(good, po, rng, None, fake, fake, None) == -1
+
+
+def test_library_reads_no_environment_variables():
+    """kernel selection is a function of the structs only (no hidden dispatch): no translation unit of the library
+    calls getenv (the statically linked CUDA runtime does, for its own CUDA_* variables)"""
+    csrc = os.path.join(ROOT, "sde_mc_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".in")):
+            assert "getenv" not in open(os.path.join(csrc, name)).read(), name
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -138,13 +138,12 @@ def test_short_path_kernel_matches_generic_kernel(case, monkeypatch):
     n = 300_001  # ragged: the last warp is partial and lanes run out of paths at different times
     lib = L.load()
     res = {}
-    monkeypatch.setenv("SDEMC_JUMP_FLAT_PACKED", "0")   # the variant that keeps jump_kernel's streams
-    for flat in ("0", "1"):
-        monkeypatch.setenv("SDEMC_JUMP_FLAT", flat)
+    for flat, short in (("0", L.SHORT_OFF), ("1", L.SHORT_ALIGNED)):   # ALIGNED keeps jump_kernel's streams
+        solver.short_path = short
         with torch.cuda.device(DEV):
             mom = E.Moments(torch.device(DEV, 0))
             po = _spec.payoff_struct(payoff, math.exp(-0.06), mode)
-            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(7, 123, n), L.ptr(mom.buf),
+            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(7, 123, n), None, L.ptr(mom.buf),
                                          L.ptr(L.workspace(torch.device(DEV, 0))), L.stream_ptr(torch.device(DEV, 0))))
             res[flat] = mom.read()
     a, b = res["0"], res["1"]
@@ -170,9 +169,10 @@ def test_persistent_lane_pair_kernel_matches_lockstep_pair_kernel(case, monkeypa
                     "levy2d_4_2_exact": (4, 2)}[case]
     n = 200_003
     res = {}
-    for flat in ("0", "1"):
-        monkeypatch.setenv("SDEMC_PAIR_FLAT", flat)
+    from sde_mc_b200 import _lib as L
+    for flat, short in (("0", L.SHORT_OFF), ("1", L.SHORT_ALIGNED)):
         solver = sm.JumpEulerSolver(sde, 3, coarse, device=DEV, exact_jumps=case.endswith("exact"), seed=11)
+        solver.short_path = short
         res[flat] = _level_moments(solver, payoff, sm.ConstantShortRate(0.02), n, fine, coarse).read()
     a, b = res["0"], res["1"]
     assert a["n"] == b["n"] == n
@@ -198,13 +198,13 @@ def test_packed_short_path_kernel_same_law_as_generic_kernel(steps, mode, monkey
     n = 20_000_001
     lib = L.load()
     res = {}
-    for name, flat in (("generic", "0"), ("packed", "1")):
-        monkeypatch.setenv("SDEMC_JUMP_FLAT", flat)
+    for name, short in (("generic", L.SHORT_OFF), ("packed", L.SHORT_PACKED)):
+        solver.short_path = short
         with torch.cuda.device(DEV):
             dev = torch.device(DEV, 0)
             mom = E.Moments(dev)
             po = _spec.payoff_struct(payoff, math.exp(-0.06), idx)
-            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(5, 1000, n), L.ptr(mom.buf),
+            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(5, 1000, n), None, L.ptr(mom.buf),
                                          L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
             res[name] = mom.read()
     a, b = res["generic"], res["packed"]
@@ -225,7 +225,7 @@ def test_packed_short_path_kernel_same_law_as_generic_kernel(steps, mode, monkey
 
 @pytest.mark.parametrize("steps,exact", [(1, False), (1, True), (4, False)])
 def test_packed_kernel_restated_iteration_matches_generic_iteration(steps, exact, monkeypatch):
-    """Same packed stream, two forms of the loop body: the generic jump_iteration (SDEMC_JUMP_FLAT_PACKED=2) and the
+    """Same packed stream, two forms of the loop body: the generic jump_iteration (SDEMC_SHORT_PACKED_GENERIC) and the
     restated one (stateless mesh, sigma^2 dt folded into the Box-Muller radius, one-FMA hit test; default).  Same
     draws, same mesh, same hits: iteration totals and all five moment sums equal up to fp32 rounding of the states."""
     from sde_mc_b200 import _engine as E
@@ -235,15 +235,14 @@ def test_packed_kernel_restated_iteration_matches_generic_iteration(steps, exact
     solver = sm.JumpEulerSolver(sde, 3, steps, device=DEV, exact_jumps=exact)
     n = 3_000_001
     lib = L.load()
-    monkeypatch.setenv("SDEMC_JUMP_FLAT", "1")
     res = {}
-    for mode in ("2", "1"):
-        monkeypatch.setenv("SDEMC_JUMP_FLAT_PACKED", mode)
+    for mode, short in (("2", L.SHORT_PACKED_GENERIC), ("1", L.SHORT_PACKED)):
+        solver.short_path = short
         with torch.cuda.device(DEV):
             dev = torch.device(DEV, 0)
             mom = E.Moments(dev)
             po = _spec.payoff_struct(sm.EuroCall(1.0), math.exp(-0.06), L.INDEX_ADAPTED)
-            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(9, 77, n), L.ptr(mom.buf),
+            L.check(lib.sdemc_mc_moments(solver._sde_struct(steps), po, L.SdemcRange(9, 77, n), None, L.ptr(mom.buf),
                                          L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
             res[mode] = mom.read()
     a, b = res["2"], res["1"]

@@ -16,9 +16,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _solve(solver_factory, bs, row_align):
+def _solve(solver_factory, bs, row_align, tma=True):
     solver = solver_factory()
     solver.row_align = row_align
+    solver.tma_store = tma                    # sdemc_paths_out.flags: SDEMC_OUT_NO_TMA
     out = solver.solve(bs=bs)
     return out
 
@@ -35,11 +36,7 @@ def test_diffusion_store_paths_identical_across_layouts(bs, steps):
     assert p_dense.is_contiguous() and n_dense.is_contiguous()
     assert torch.equal(p_tma, p_dense) and torch.equal(n_tma, n_dense)
     assert torch.isfinite(p_tma).all() and float(p_tma[:, 0].min()) == 1.0
-    os.environ["SDEMC_NO_TMA_STORE"] = "1"          # padded pitch -> 16-byte vector flush of the LSU kernel
-    try:
-        p_vec, n_vec = _solve(factory, bs, 32)
-    finally:
-        del os.environ["SDEMC_NO_TMA_STORE"]
+    p_vec, n_vec = _solve(factory, bs, 32, tma=False)   # padded pitch -> 16-byte vector flush of the LSU kernel
     assert torch.equal(p_vec, p_dense) and torch.equal(n_vec, n_dense)
 
 

@@ -66,9 +66,10 @@ def test_user_library_builds_and_exports_entry_points():
     # wrong model shape is refused before any CUDA call
     other = _spec.sde_struct(_spec.spec_of(sm.Gbm(0.02, 0.3, torch.tensor([1.0]), 1)), 3.0, 10)
     lib.sdemc_user_mc_moments.argtypes = [ctypes.POINTER(L.SdemcSde), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                          ctypes.c_void_p, ctypes.c_void_p]
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     rng = L.SdemcRange(1, 0, 4)
-    assert lib.sdemc_user_mc_moments(other, None, ctypes.cast(ctypes.pointer(rng), ctypes.c_void_p), None, None, None) == -2
+    assert lib.sdemc_user_mc_moments(other, None, ctypes.cast(ctypes.pointer(rng), ctypes.c_void_p), None, None, None,
+                                     None) == -2
 
 
 def test_bad_expression_reports_the_compiler_error():
