@@ -166,7 +166,18 @@ def check(rc):
         msg = lib.sdemc_strerror(rc).decode()
         if rc == -3:
             msg += " [" + lib.sdemc_last_cuda_error().decode() + "]"
+        rearm_workspaces()
         raise SdemcError("sdemc error %d: %s" % (rc, msg))
+
+
+def rearm_workspaces():
+    """A launch that failed mid-grid leaves the reduction ticket of its workspace part-counted; zero every workspace
+    so that later reductions on those streams start clean."""
+    for ws in _workspaces.values():
+        try:
+            ws.zero_()
+        except RuntimeError:      # the CUDA context itself is gone: nothing left to protect
+            pass
 
 
 def require_cuda(device):

@@ -92,8 +92,51 @@ def sde_struct(spec, T, num_steps, max_jumps=0, exact_jumps=False, jump_strategy
     return s
 
 
+# ---- whose coefficients are these? -----------------------------------------------------------------------------------
+# The reference always calls the Python methods of an Sde / Option, so a user subclass that overrides one of them
+# changes the model (class Cev(Gbm) with a new diffusion(), class MyCall(EuroCall) with a new payoff()).  The
+# kernel_spec() of a built-in class describes the built-in model only: it may not be used when a user class -- any
+# class outside this package, more derived than the built-in -- overrides a method the reference's loop would call,
+# unless that user class restates the coefficients itself (kernel_spec / kernel_code at the same level or below).
+_SDE_METHODS = ("drift", "diffusion", "jumps", "sample_jumps", "jump_mean", "jump_rate")
+_OPTION_METHODS = ("payoff", "transform", "__call__")
+_PACKAGE = __name__.rsplit(".", 1)[0]
+
+
+def _user_classes(obj):
+    """the classes of the object's MRO that are more derived than the first class of this package"""
+    out = []
+    for cls in type(obj).__mro__:
+        if cls.__module__ == _PACKAGE or cls.__module__.startswith(_PACKAGE + "."):
+            break
+        out.append(cls)
+    return out
+
+
+def user_overrides(obj, names, restated_by):
+    """(overridden, restated): the methods among `names` that user classes override WITHOUT restating the kernel
+    coefficients (an attribute of `restated_by`) at that level or further down the hierarchy, and whether any user
+    class restates them at all"""
+    over = []
+    for cls in _user_classes(obj):
+        if any(a in cls.__dict__ for a in restated_by):
+            return over, True
+        over += [n for n in names if n in cls.__dict__]
+    return over, False
+
+
+def payoff_kernel_spec(payoff):
+    """the payoff's kernel_spec method when the fused kernels evaluate exactly what its Python payoff computes, else
+    None (user-defined Option, or a subclass of a built-in that overrides payoff / transform: those run as Python
+    on stored trajectories, mc._mc_simple_python_payoff)"""
+    fn = getattr(payoff, "kernel_spec", None)
+    if fn is None or user_overrides(payoff, _OPTION_METHODS, ("kernel_spec",))[0]:
+        return None
+    return fn
+
+
 def payoff_struct(payoff, discount_factor, index_mode):
-    spec = getattr(payoff, "kernel_spec", None)
+    spec = payoff_kernel_spec(payoff)
     if spec is None:
         raise L.SdemcError("payoff %r is not one of the built-in Option classes; the fused kernels cannot evaluate "
                            "arbitrary Python payoffs (no CPU fallback)" % type(payoff).__name__)
@@ -120,4 +163,12 @@ def spec_of(sde):
     if fn is None:
         raise L.SdemcError("%s does not publish kernel coefficients; only the built-in SDE classes run on the B200 "
                            "engine (no CPU fallback)" % type(sde).__name__)
+    over, restated = user_overrides(sde, _SDE_METHODS, ("kernel_spec", "kernel_code"))
+    if over:
+        raise L.SdemcError("%s overrides %s but inherits the kernel coefficients of a parent class; the fused kernels "
+                           "would simulate the parent model.  Define kernel_code() on the subclass (see "
+                           "Sde.kernel_spec); there is no CPU fallback" % (type(sde).__name__, ", ".join(over)))
+    if restated and not any("kernel_spec" in c.__dict__ for c in _user_classes(sde)):
+        from .sde import Sde                       # the user's kernel_code() describes the model: USER family
+        return Sde.kernel_spec(sde)
     return fn()

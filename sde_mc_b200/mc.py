@@ -64,7 +64,7 @@ def mc_simple(num_trials, sde_solver, payoff, discounter=None, bs=None, return_n
         discounter = ConstantShortRate(r=0.0)
     num_trials = int(num_trials)
     start = time.time()
-    if getattr(payoff, "kernel_spec", None) is None:
+    if _spec.payoff_kernel_spec(payoff) is None:
         return _mc_simple_python_payoff(num_trials, sde_solver, payoff, discounter, bs, payoff_time, start)
     if not bs:
         po = _spec.payoff_struct(payoff, float(discounter(sde_solver.time_interval)), _index_mode(payoff_time))
@@ -133,6 +133,8 @@ def mc_terminal_cv(num_trials, sde_solver, payoff, discounter=None, bs=None, ret
         _sync(sde_solver)
         return MCStatistics(mean, stderr, time.time() - start, num_trials, out, payoffs, normals)
     first = min(int(bs), num_trials)
+    if first < 2:
+        raise ValueError("mc_terminal_cv estimates beta from the first batch: bs and num_trials must be at least 2")
     a = E.run_moments(sde_solver, payoff, discounter, first, L.INDEX_ADAPTED).read()
     cov = (a['sum_pc'] - a['sum'] * a['sum_c'] / first) / (first - 1)
     var_c = (a['sumsq_c'] - a['sum_c'] ** 2 / first) / (first - 1)
@@ -153,7 +155,8 @@ def mc_apply_cvs(models, solver, trials, payoff, discounter, sim_bs=1e5, bs=1000
     are applied with PyTorch on the GPU."""
     start = time.time()
     trials = int(trials)
-    if fused_cv_supported(models, solver, tol) and isinstance(discounter, ConstantShortRate):
+    if (fused_cv_supported(models, solver, tol) and isinstance(discounter, ConstantShortRate)
+            and _spec.payoff_kernel_spec(payoff) is not None):
         mom = mc_cv_fused(models, solver, trials, payoff, discounter).read()
         mean, stderr = E.mean_and_stderr(mom['sum'], mom['sumsq'], trials)
         return MCStatistics(mean, stderr, time.time() - start, trials)

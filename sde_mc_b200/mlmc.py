@@ -16,11 +16,21 @@ from .helpers import mc_estimates
 from .mc import MCStatistics
 
 
+def _pair_lib(solver):
+    """the library with the coupled-pair entry point for this solver's model, or a clear error: JIT-built user models
+    and the Heston scheme have no pair kernels (the reference's Heston solver could run multilevel_solve)"""
+    spec = _spec.spec_of(solver.sde)
+    if spec.family in (L.FAMILY_USER, L.FAMILY_HESTON) or spec.asian:
+        raise L.SdemcError("MLMC pair kernels (mc_multilevel, get_optimal_trials, multilevel_solve) exist for the "
+                           "built-in geometric / arithmetic models only, not for %s" % type(solver.sde).__name__)
+    return L.load()
+
+
 def _level_moments(solver, payoff, discounter, trials, fine, coarse):
     """moments of D(T) (P(fine) - P(coarse)) over `trials` coupled pairs (coarse == 0: single level)."""
     trials = int(trials)
     dev = solver._compute_device()
-    lib = L.load()
+    lib = _pair_lib(solver)
     rank, size = E.world()
     lo = solver._take_paths(trials)
     off, cnt = E.shard(trials, rank, size)
@@ -108,7 +118,7 @@ def mlmc_bs_from_trials(trials, levels, max_mem=5 * 10 ** 8, dim=1, max_jumps=0)
 def _pair_terminals(solver, bs, levels, inject):
     fine, coarse = int(levels[0]), int(levels[1])
     dev = solver._compute_device()
-    lib = L.load()
+    lib = _pair_lib(solver)
     d = solver.sde.dim
     sde = solver._sde_struct(fine)
     keep = []

@@ -287,7 +287,8 @@ class AsianWrapper(Sde):
         return self.base_sde.jump_rate()
 
     def kernel_spec(self):
-        base = self.base_sde.kernel_spec()
+        from ._spec import spec_of
+        base = spec_of(self.base_sde)
         if base.dim != 1 or base.m != 1 or base.family == L.FAMILY_HESTON:
             raise L.SdemcError("AsianWrapper kernels exist for 1-D 'diag' base SDEs only")
         spec = KernelSpec(family=base.family, dim=2, m=1, marks=base.marks, asian=1)

@@ -186,8 +186,11 @@ def fused_cv_supported(models, solver, tol=0):
     (Gbm, Merton), constant short rate, tol == 0."""
     if tol != 0 or solver.sde.dim != 1 or solver.sde.diffusion_struct != 'diag':
         return False
-    spec = getattr(solver.sde, 'kernel_spec', None)
-    if spec is None or spec().family != L.FAMILY_GEOMETRIC or spec().asian:
+    try:
+        spec = _spec.spec_of(solver.sde)
+    except L.SdemcError:
+        return False
+    if spec.family != L.FAMILY_GEOMETRIC or spec.asian:
         return False
     if not FUSED_CV_ENABLED:
         return False

@@ -15,6 +15,7 @@ import torch
 
 from common import ROOT, golden, golden_json, rel_err, sm, t
 from sde_mc_b200 import _lib as L
+from sde_mc_b200 import _spec
 
 
 # ---- API surface -------------------------------------------------------------------------------------------------
@@ -328,7 +329,7 @@ def test_no_cpu_fallback():
 def test_bench_reference_arm_prints_exactly_one_json_line():
     """bench.py contract: rank 0 prints ONE JSON line on stdout (everything else -- progress, native libraries such as
     NCCL's version banner -- goes to stderr).  The reference arm runs without a GPU: the reference's CPU algorithm
-    (oracle/torch_port.py) on a bounded sample of the default workload."""
+    (the unmodified package in oracle/_ref, else oracle/torch_port.py) on a bounded sample of the default workload."""
     import json
     import subprocess
     import sys
@@ -341,6 +342,50 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "path_steps_per_sec" and d["unit"] == "path-steps/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference from oracle/_ref where `make -C oracle ref` installed it, else the pinned port
+    have_ref = os.path.isdir(os.path.join(root, "oracle", "_ref", "sde_mc"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["config"]["workload"] == "gbm_1d_eurocall_euler_1e9x252"
+    assert d["config"]["workload"] == "merton_1d_eurocall_jump_adapted_euler_1e9x100"     # the north-star config
+
+
+def test_subclass_overrides_are_not_silently_replaced_by_the_parents_kernels():
+    """The reference always calls the Python methods, so a subclass that overrides one changes the model.  The
+    parent's kernel_spec() must then not be used: payoffs fall back to Python-on-stored-paths, SDEs need their own
+    kernel_code()."""
+    class Capped(sm.EuroCall):
+        def payoff(self, x):
+            return torch.clamp(super().payoff(x), max=0.5)
+
+    class Shifted(sm.EuroCall):                       # overrides nothing the loop calls: still the built-in
+        def describe(self):
+            return "call"
+
+    assert _spec.payoff_kernel_spec(sm.EuroCall(1.0)) is not None
+    assert _spec.payoff_kernel_spec(Shifted(1.0)) is not None
+    assert _spec.payoff_kernel_spec(Capped(1.0)) is None
+    with pytest.raises(L.SdemcError):
+        _spec.payoff_struct(Capped(1.0), 1.0, L.INDEX_ADAPTED)
+
+    class Cev(sm.Gbm):
+        def diffusion(self, t, x):
+            return self.sigma * torch.sqrt(torch.clamp(x, min=0))
+
+    class CevWithCode(Cev):
+        def kernel_code(self):
+            return dict(drift=["p[0] * x[0]"], diffusion=["p[1] * sqrtf(fmaxf(x[0], 0.f))"], params=[0.02, 0.3])
+
+    class CodeThenOverride(CevWithCode):              # kernel_code describes CevWithCode, not this class
+        def drift(self, t, x):
+            return 0 * x
+
+    x0 = torch.tensor([1.0])
+    assert _spec.spec_of(sm.Gbm(0.02, 0.3, x0, 1)).family == L.FAMILY_GEOMETRIC
+    with pytest.raises(L.SdemcError) as e:
+        _spec.spec_of(Cev(0.02, 0.3, x0, 1))
+    assert "diffusion" in str(e.value) and "Cev" in str(e.value)
+    assert _spec.spec_of(CevWithCode(0.02, 0.3, x0, 1)).family == L.FAMILY_USER
+    with pytest.raises(L.SdemcError):
+        _spec.spec_of(CodeThenOverride(0.02, 0.3, x0, 1))
+    with pytest.raises(L.SdemcError):                 # wrappers look through to the wrapped model
+        _spec.spec_of(sm.AsianWrapper(Cev(0.02, 0.3, x0, 1)))
