@@ -257,6 +257,18 @@ int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rat
                 const sdemc_mlp* f, const sdemc_mlp* g, const sdemc_range* range, const sdemc_inject* inject,
                 sdemc_moments* d_moments, float* d_gamma_out /* (n) or NULL */, void* d_workspace, void* stream);
 
+/* Test hook: the noise of `range`'s paths exactly as the kernels compute it from Philox (same device functions, same
+ * fp32 / MUFU arithmetic), `count` values per path and array, row-major (n, count):
+ *   BROWNIAN : d_a = unit normals of the Brownian stream in consumption order
+ *   QUEUE    : d_a = cumulative jump times, d_b = raw mark draws of the QUEUE strategy (jump j of the path)
+ *   INLINE   : d_a = Exp(1) gap candidate, d_b = raw mark candidate of iteration k (INLINE strategy)
+ *   PACKED   : d_a = Brownian unit normal, d_b = gap candidate, d_c = raw mark candidate of iteration k (SHORT_PACKED)
+ * Raw mark draws are N(0,1) for LOGNORMAL and U[0,1) for ICDF marks, as in sdemc_inject.d_marks.  Feeding these
+ * arrays to the reference's loop (or the oracle) must reproduce what the moments kernels report per path. */
+typedef enum { SDEMC_DRAWS_BROWNIAN = 0, SDEMC_DRAWS_QUEUE = 1, SDEMC_DRAWS_INLINE = 2, SDEMC_DRAWS_PACKED = 3 } sdemc_draws_kind;
+int sdemc_debug_draws(const sdemc_sde* sde, const sdemc_range* range, int32_t kind, int32_t count, float* d_a,
+                      float* d_b, float* d_c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ INDEX_TERMINAL, INDEX_ADAPTED = 0, 1
  PAYOFF_DIGITAL, PAYOFF_ASIAN_CALL, PAYOFF_HESTON_RAINBOW, PAYOFF_BEST_OF) = range(10)
 
 
+DRAWS_BROWNIAN, DRAWS_QUEUE, DRAWS_INLINE, DRAWS_PACKED = range(4)
 SHORT_AUTO, SHORT_OFF, SHORT_ALIGNED, SHORT_PACKED, SHORT_PACKED_GENERIC = range(5)
 OUT_NO_TMA = 1
 
@@ -104,6 +105,8 @@ _SIGNATURES = {
     "sdemc_abi_layout": (C.c_int, [C.POINTER(C.c_uint32), C.c_int]),
     "sdemc_mc_moments": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.POINTER(SdemcRange),
                                    C.POINTER(SdemcPathsOut), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdemc_debug_draws": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcRange), C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdemc_eval_payoff": (C.c_int, [C.POINTER(SdemcPayoff), C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "sdemc_solve_paths": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.POINTER(SdemcRange),
                                     C.POINTER(SdemcInject), C.POINTER(SdemcPathsOut), C.c_void_p, C.c_void_p]),

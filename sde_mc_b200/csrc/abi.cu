@@ -139,6 +139,20 @@ int sdemc_mc_moments(const sdemc_sde* sde, const sdemc_payoff* payoff, const sde
 }
 
 
+int sdemc_debug_draws(const sdemc_sde* sde, const sdemc_range* range, int32_t kind, int32_t count, float* d_a,
+                      float* d_b, float* d_c, void* stream) {
+  if (!valid_sde(sde) || !sized(range) || kind < SDEMC_DRAWS_BROWNIAN || kind > SDEMC_DRAWS_PACKED || count < 1 || !d_a)
+    return SDEMC_ERR_BAD_ARG;
+  if (kind != SDEMC_DRAWS_BROWNIAN && (!d_b || sde->marks == SDEMC_MARKS_NONE)) return SDEMC_ERR_BAD_ARG;
+  if (kind == SDEMC_DRAWS_PACKED && !d_c) return SDEMC_ERR_BAD_ARG;
+  if (range->n_paths == 0) return SDEMC_OK;
+  DevRange rg;
+  rg.path_lo = range->path_lo;
+  rg.n_paths = range->n_paths;
+  return launch_debug_draws(*sde, rg, make_philox_keys(range->seed), kind, count, d_a, d_b, d_c,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
 int sdemc_eval_payoff(const sdemc_payoff* payoff, int32_t dim, const float* d_x, uint64_t n, float* d_out, void* stream) {
   if (!sized(payoff) || dim < 1 || dim > SDEMC_MAX_DIM || (n > 0 && (!d_x || !d_out))) return SDEMC_ERR_BAD_ARG;
   if (n == 0) return SDEMC_OK;

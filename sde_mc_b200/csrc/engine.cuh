@@ -77,10 +77,13 @@ struct DevPerPath {
   float* payoffs;
   int* iters;
   float* terminal;
-  __device__ __forceinline__ bool any() const { return payoffs != nullptr || iters != nullptr || terminal != nullptr; }
+  __host__ __device__ __forceinline__ bool any() const { return payoffs != nullptr || iters != nullptr || terminal != nullptr; }
 };
 template <int DIM, class X>
 __device__ __forceinline__ void write_per_path(const DevPerPath& pp, uint64_t i, float pay, int iters, const X& xp) {
+#ifdef SDEMC_NO_PER_PATH  // A/B builds only (tools/build_variant.sh): what the per-path hook costs the hot loops
+  return;
+#endif
   if (pp.payoffs) pp.payoffs[i] = pay;
   if (pp.iters) pp.iters[i] = iters;
   if (pp.terminal) {
@@ -257,11 +260,13 @@ __device__ __forceinline__ void add_jump(const DevSde& s, float (&x)[kMaxDim], c
 // ------------------------------------------------------------------------------------------------------------
 // payoff  (Option.__call__ options.py:167-176; payoffs options.py:196-321)
 // ------------------------------------------------------------------------------------------------------------
+// exp / log are the full-precision expf / logf (1 ulp): the payoff runs once per path, so their cost is nil, and the
+// 54 reference vectors hold at 2e-6 (the 2-ulp intrinsics do not, for the geometric basket and log-price payoffs).
 template <int DIM>
 __device__ __forceinline__ float eval_payoff(const DevPayoff& po, const float (&xin)[kMaxDim]) {
   float x[kMaxDim];
 #pragma unroll
-  for (int i = 0; i < DIM; ++i) x[i] = po.tdisc * (po.log ? __expf(xin[i]) : xin[i]);
+  for (int i = 0; i < DIM; ++i) x[i] = po.tdisc * (po.log ? expf(xin[i]) : xin[i]);
   const float K = po.strike;
   float sp, r;
   switch (po.kind) {
@@ -276,10 +281,10 @@ __device__ __forceinline__ float eval_payoff(const DevPayoff& po, const float (&
       r = sp > K ? sp - K : 0.0f;
       break;
     case SDEMC_PAYOFF_BASKET_GEOM:
-      sp = __logf(x[0]);
+      sp = logf(x[0]);
 #pragma unroll
-      for (int i = 1; i < DIM; ++i) sp += __logf(x[i]);
-      sp = __expf(sp / (float)DIM);
+      for (int i = 1; i < DIM; ++i) sp += logf(x[i]);
+      sp = expf(sp / (float)DIM);
       r = sp > K ? sp - K : 0.0f;
       break;
     case SDEMC_PAYOFF_RAINBOW:
@@ -291,7 +296,7 @@ __device__ __forceinline__ float eval_payoff(const DevPayoff& po, const float (&
     case SDEMC_PAYOFF_DIGITAL: r = x[0] > K ? 1.0f : 0.0f; break;
     case SDEMC_PAYOFF_ASIAN_CALL:
       sp = DIM > 1 ? x[DIM > 1 ? 1 : 0] / po.aux : 0.0f;
-      if (po.log) sp = __expf(sp);
+      if (po.log) sp = expf(sp);
       r = sp > K ? sp - K : 0.0f;
       break;
     case SDEMC_PAYOFF_HESTON_RAINBOW:

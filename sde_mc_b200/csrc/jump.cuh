@@ -67,27 +67,37 @@ struct InjectJumps {
 // iteration): draws `qd` more (tau, J) pairs into this thread's queue column and returns the new running jump time.
 // Two Philox blocks give 4 jumps: 4 gap uniforms + 4 mark draws (2 Box-Muller pairs or 4 uniforms).
 // PREMUL: queue c[0] * J instead of J (1-D moments kernel, jump1d.cuh).
+// The draws of queue group `grp` (global index: chunk * groups + r), i.e. jumps 4 grp .. 4 grp + 3 of the path: four
+// Exp(1) gaps from block 2 grp, four raw mark draws from block 2 grp + 1 (two Box-Muller pairs for lognormal marks,
+// four uniforms for icdf marks).  Shared by queue_refill and the draw-reporting test hook (debug_draws.cuh).
+template <int MARKS>
+__device__ __forceinline__ void queue_group_draws(uint32_t grp, uint32_t plo, uint32_t phi, const PhiloxKeys& keys,
+                                                  float (&gap)[4], float (&raw)[4]) {
+  uint32_t g[4], m[4];
+  philox4x32_10(grp * 2u, STREAM_JUMP_QUEUE, plo, phi, keys, g);
+  philox4x32_10(grp * 2u + 1u, STREAM_JUMP_QUEUE, plo, phi, keys, m);
+  if (MARKS == SDEMC_MARKS_LOGNORMAL) {
+    box_muller(m[0], m[1], raw[0], raw[1]);
+    box_muller(m[2], m[3], raw[2], raw[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) raw[j] = bits_to_u01(m[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) gap[j] = exp1_from_bits(g[j]);
+}
+
 template <int MARKS, bool PREMUL = false>
 __device__ __noinline__ float queue_refill(int qd, uint32_t chunk, uint32_t plo, uint32_t phi, float tau_acc) {
   const DevSde& s = g_sh_sde;
   const PhiloxKeys& keys = g_sh_keys;
   const int groups = qd >> 2;
   for (int r = 0; r < groups; ++r) {
-    uint32_t g[4], m[4];
-    const uint32_t blk = (chunk * (uint32_t)groups + (uint32_t)r) * 2u;
-    philox4x32_10(blk, STREAM_JUMP_QUEUE, plo, phi, keys, g);
-    philox4x32_10(blk + 1u, STREAM_JUMP_QUEUE, plo, phi, keys, m);
-    float raw[4];
-    if (MARKS == SDEMC_MARKS_LOGNORMAL) {
-      box_muller(m[0], m[1], raw[0], raw[1]);
-      box_muller(m[2], m[3], raw[2], raw[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) raw[j] = bits_to_u01(m[j]);
-    }
+    float gap[4], raw[4];
+    queue_group_draws<MARKS>(chunk * (uint32_t)groups + (uint32_t)r, plo, phi, keys, gap, raw);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      tau_acc = fmaf(exp1_from_bits(g[j]), s.inv_rate, tau_acc);
+      tau_acc = fmaf(gap[j], s.inv_rate, tau_acc);
       const float mark = mark_from_raw<MARKS>(s, raw[j]);
       jump_queue_smem[(r * 4 + j) * blockDim.x + threadIdx.x] = make_float2(tau_acc, PREMUL ? s.c[0] * mark : mark);
     }
@@ -148,19 +158,24 @@ struct InlineJumps {
   }
   // one Philox block serves two consecutive iterations: (gap, mark) from words (0, 1) and (2, 3) for uniform
   // marks; two gaps and one Box-Muller pair for lognormal marks.  k is the same for all active lanes of a warp.
+  // the (gap, raw mark) candidates of iterations 2b and 2b + 1 from block b of STREAM_JUMP_INLINE
+  static __device__ __forceinline__ void block_draws(uint32_t b, uint32_t plo, uint32_t phi, const PhiloxKeys& keys,
+                                                     float& gap0, float& raw0, float& gap1, float& raw1) {
+    uint32_t o[4];
+    philox4x32_10(b, STREAM_JUMP_INLINE, plo, phi, keys, o);
+    gap0 = exp1_from_bits(o[0]);
+    if (MARKS == SDEMC_MARKS_LOGNORMAL) {
+      gap1 = exp1_from_bits(o[1]);
+      box_muller(o[2], o[3], raw0, raw1);
+    } else {
+      raw0 = bits_to_u01(o[1]);
+      gap1 = exp1_from_bits(o[2]);
+      raw1 = bits_to_u01(o[3]);
+    }
+  }
   __device__ __forceinline__ void begin_iter(const DevSde&, const PhiloxKeys& keys, int k) {
     if ((k & 1) == 0) {
-      uint32_t o[4];
-      philox4x32_10((uint32_t)(k >> 1), STREAM_JUMP_INLINE, plo, phi, keys, o);
-      cand_gap = exp1_from_bits(o[0]);
-      if (MARKS == SDEMC_MARKS_LOGNORMAL) {
-        next_gap = exp1_from_bits(o[1]);
-        box_muller(o[2], o[3], cand_raw, next_raw);
-      } else {
-        cand_raw = bits_to_u01(o[1]);
-        next_gap = exp1_from_bits(o[2]);
-        next_raw = bits_to_u01(o[3]);
-      }
+      block_draws((uint32_t)(k >> 1), plo, phi, keys, cand_gap, cand_raw, next_gap, next_raw);
     } else {
       cand_gap = next_gap;
       cand_raw = next_raw;

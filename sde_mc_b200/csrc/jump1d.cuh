@@ -9,6 +9,8 @@
 //     clamp that replaces the reference's assert :193).
 //   * sigma^2 and dt are folded into the Box-Muller radius (one square root per iteration instead of sqrt(dt) plus
 //     the radius root), the jump coefficient into the queued mark (c J).
+//   * the hit test |tau - t| <= 1e-12 + 1e-5 |t| is evaluated bit for bit as in jump.cuh, so iteration counts and
+//     hit iterations are those of the path-storing kernel (and of the reference on the same draws).
 //   * the queue of pre-drawn (tau, c J) pairs is popped branch-free by bumping a shared-memory address on a hit.
 //     Whether a path ran out of queued jumps is checked once per group of 6 iterations (one Philox block of
 //     normals): the group runs speculatively from a saved (x, t, queue head); if the head left the filled part of
@@ -78,9 +80,11 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
       const float g = fmaf(fast_sqrt(r2 * dt), cs, a * dt);
       const float xn = GEO ? fmaf(x, g, x) : x + g;
       t += dt;
-      // torch.isclose(tau, t, atol=1e-12) with its default rtol=1e-5 (:212,225).  t never exceeds tau by more than
-      // an ulp (dt <= tau - t), so |tau - t| <= 1e-12 + 1e-5 |t|  <=>  t (1 + 1e-5) + 1e-12 >= tau.
-      bool hit = fmaf(t, 1.00001f, 1e-12f) >= e.x;
+      // torch.isclose(tau, t, atol=1e-12) with its default rtol=1e-5 (:212,225), evaluated exactly as jump.cuh and
+      // the reference do (t >= 0).  The one-FMA form t (1 + 1e-5) + 1e-12 >= tau used here in round 1 rounds its
+      // threshold differently: about one path in 1e6 then hit a jump one iteration early -- or, for a jump 1e-5 T
+      // after T, hit a jump the reference never applies (found by tests/test_gpu_fastpath.py).
+      bool hit = fabsf(e.x - t) <= fmaf(t, 1e-5f, 1e-12f);
       if (decltype(masked)::value) hit = hit && active;
       const float Jc = hit ? e.y : 0.0f;
       if (GEO) x = fmaf(EXACT ? xn : x, Jc, xn);

@@ -123,8 +123,26 @@ struct PackedJumps {
   __device__ __forceinline__ float mark(const DevSde&, int) const { return J; }
 };
 
+// One block of STREAM_PACKED = the draws of iterations 2b, 2b + 1: log2 of the Brownian radius uniform and the (cos,
+// sin) of its angle (z = sqrt(-2 ln2 lg_z) * cs_z[.]), two Exp(1) gap candidates, two N(0,1) mark candidates.
+__device__ __forceinline__ void packed_block_draws(uint32_t b, uint32_t plo, uint32_t phi, const PhiloxKeys& keys,
+                                                   float& lg_z, float (&cs_z)[2], float (&gap)[2], float (&raw)[2]) {
+  uint32_t o[4];
+  philox4x32_10(b, STREAM_PACKED, plo, phi, keys, o);
+  const float ang_z = fmaf(angle_bits_to_12(o[3]), 804.247719318987f, -804.247719318987f);
+  const float ang_m = fmaf(__uint_as_float((o[3] >> 16) | 0x3f800000u), 804.247719318987f, -804.247719318987f);
+  lg_z = fast_lg2(bits_to_u01_open0(o[0]));
+  const float r_m = fast_sqrt(fast_lg2(bits_to_u01_open0(o[1])) * -1.3862943611198906f);
+  cs_z[0] = fast_cos(ang_z);
+  cs_z[1] = fast_sin(ang_z);
+  raw[0] = r_m * fast_cos(ang_m);
+  raw[1] = r_m * fast_sin(ang_m);
+  gap[0] = exp1_from_bits(o[2]);
+  gap[1] = exp1_from_bits((o[0] >> 23) | ((o[1] >> 23) << 9) | ((o[2] >> 23) << 18));  // low 23 bits are used
+}
+
 // FAST: the iteration in the restated form of jump1d.cuh -- stateless mesh, sigma^2 and dt folded into the Box-Muller
-// radius (one square root per iteration), one-FMA hit test, the jump coefficient folded into the mark -- about 15
+// radius (one square root per iteration), the jump coefficient folded into the mark -- about 16
 // instructions instead of the ~45 of the generic jump_iteration (geometric Euler only; Milstein takes the generic
 // form).  Same draws, same mesh and hits; the state agrees to fp32 rounding (test: sums to 1e-5, iterations equal).
 template <class C, bool FAST>
@@ -162,17 +180,8 @@ __global__ void __launch_bounds__(256, 3)
 
   StepRecord rec_unused;
   while (live) {
-    uint32_t o[4];
-    philox4x32_10((uint32_t)(st.k >> 1), STREAM_PACKED, plo, phi, keys, o);  // st.k is even at a group start
-    const float ang_z = fmaf(angle_bits_to_12(o[3]), 804.247719318987f, -804.247719318987f);
-    const float ang_m = fmaf(__uint_as_float((o[3] >> 16) | 0x3f800000u), 804.247719318987f, -804.247719318987f);
-    const float lg_z = fast_lg2(bits_to_u01_open0(o[0]));
-    const float r_m = fast_sqrt(fast_lg2(bits_to_u01_open0(o[1])) * -1.3862943611198906f);
-    const float cs_z[2] = {fast_cos(ang_z), fast_sin(ang_z)};
-    src.cand_raw[0] = r_m * fast_cos(ang_m);
-    src.cand_raw[1] = r_m * fast_sin(ang_m);
-    src.cand_gap[0] = exp1_from_bits(o[2]);
-    src.cand_gap[1] = exp1_from_bits((o[0] >> 23) | ((o[1] >> 23) << 9) | ((o[2] >> 23) << 18));  // low 23 bits are used
+    float lg_z, cs_z[2];
+    packed_block_draws((uint32_t)(st.k >> 1), plo, phi, keys, lg_z, cs_z, src.cand_gap, src.cand_raw);  // st.k is even here
     if constexpr (FAST) {
       const float r2 = lg_z * (-1.3862943611198906f * s.b1[0] * s.b1[0]);  // sigma^2 (-2 ln u)
 #pragma unroll
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(256, 3)
           const float g = fmaf(fast_sqrt(r2 * dt), cs_z[sp], s.a[0] * dt);
           const float xn = fmaf(st.x[0], g, st.x[0]);
           st.t += dt;
-          const bool hit = fmaf(st.t, 1.00001f, 1e-12f) >= src.tau;               // isclose(tau, t), see jump1d.cuh
+          const bool hit = fabsf(src.tau - st.t) <= fmaf(st.t, 1e-5f, 1e-12f);    // isclose(tau, t) as in jump.cuh
           const float Jc = hit ? src.J : 0.0f;
           st.x[0] = fmaf(s.exact_jumps ? xn : st.x[0], Jc, xn);
           st.need_pop = hit;

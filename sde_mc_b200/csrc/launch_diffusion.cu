@@ -61,9 +61,9 @@ int run_store_tma(const LaunchArgs& a) {
   return SDEMC_OK;
 }
 
-template <class C, bool HESTON, bool INJECT, bool STORE>
+template <class C, bool HESTON, bool INJECT, bool STORE, bool PERPATH = false>
 int run(const LaunchArgs& a) {
-  auto kernel = diffusion_kernel<C, HESTON, INJECT, STORE>;
+  auto kernel = diffusion_kernel<C, HESTON, INJECT, STORE, PERPATH>;
   const int block = STORE ? kDiffusionStoreBlock : kBlock;
   const size_t smem = STORE ? (size_t)(block / 32) * 2 * DiffusionStoreWriter<C>::kFloats * sizeof(float) : 0;
   if (smem > 48 * 1024)
@@ -85,6 +85,7 @@ int by_mode(const LaunchArgs& a) {
     return a.use_inject ? run<C, HESTON, true, true>(a) : run<C, HESTON, false, true>(a);
   }
   if (a.use_inject) return SDEMC_ERR_UNSUPPORTED;  // injected noise is only offered with stored outputs
+  if (per_path_of_out(a.out).any()) return run<C, HESTON, false, false, true>(a);
   return run<C, HESTON, false, false>(a);
 }
 

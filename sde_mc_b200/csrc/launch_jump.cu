@@ -1,9 +1,11 @@
 // launch_jump.cu -- instantiation + dispatch of the jump-adapted kernels (jump.cuh)
 #include <type_traits>
 
+#include <algorithm>
 #include <cmath>
 
 #include "jump1d.cuh"
+#include "debug_draws.cuh"
 #include "jump_flat.cuh"
 #include "launch.cuh"
 
@@ -109,6 +111,18 @@ int by_dim(const sdemc_sde& s, const LaunchArgs& a) {
 }
 
 }  // namespace
+
+int launch_debug_draws(const sdemc_sde& s, const DevRange& rg, const PhiloxKeys& keys, int kind, int count, float* a,
+                       float* b, float* c, cudaStream_t stream) {
+  const float inv_rate = s.rate > 0.0f ? 1.0f / s.rate : 0.0f;
+  const unsigned grid = (unsigned)std::min<uint64_t>((rg.n_paths + 255) / 256, 148 * 8);
+  if (s.marks == SDEMC_MARKS_ICDF)
+    debug_draws_kernel<SDEMC_MARKS_ICDF><<<grid, 256, 0, stream>>>(rg, keys, kind, count, inv_rate, a, b, c);
+  else
+    debug_draws_kernel<SDEMC_MARKS_LOGNORMAL><<<grid, 256, 0, stream>>>(rg, keys, kind, count, inv_rate, a, b, c);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
 
 int launch_jump(const sdemc_sde& s, const LaunchArgs& a_in) {
   LaunchArgs a = a_in;
