@@ -1,22 +1,31 @@
 // jump1d.cuh -- moments-only fast path of the jump-adapted Euler loop for ONE-dimensional geometric jump diffusions
 // with sparse lognormal jumps (Merton, the north-star workload): JumpDiffusionSolver.solve solvers.py:164-226 with
 // low_storage semantics + payoff + (sum, sum^2).  Same arithmetic rules as jump.cuh (Q1-Q4 of SURVEY.md), restated
-// so that one loop iteration is ~15 instructions on top of its normal:
+// so that one loop iteration is 14 instructions on top of its normal:
 //
 //   * the mesh is stateless.  The reference keeps h = min(h, max(T - t, 0)) (:190); t never decreases, so
 //     h_k = min(h0, max(T - t_k, 0)) and  dt = min(h, tau - t) = max(min(h0, min(tau, T) - t), 0)  (fp32 subtraction
 //     of the same t is monotone, so min(T - t, tau - t) == min(T, tau) - t bit for bit; the outer max is the dt >= 0
 //     clamp that replaces the reference's assert :193).
+//   * for h0 <= 1 the clamp is the saturate modifier of the subtraction: min(h0, sat(m - t)) == max(min(h0, m - t), 0)
+//     (FADD.SAT clamps to [0, 1], and values in (h0, 1] lose against h0 anyway).
+//   * while t <= T - h0 -- i.e. in all but the last group or two of phase 1 -- min(tau, T) - t and tau - t give the
+//     same dt (both exceed h0 when tau >= T), so the cap at T is dropped there (bit-identical, one FMNMX less).
 //   * sigma^2 and dt are folded into the Box-Muller radius (one square root per iteration instead of sqrt(dt) plus
 //     the radius root), the jump coefficient into the queued mark (c J).
 //   * the hit test |tau - t| <= 1e-12 + 1e-5 |t| is evaluated bit for bit as in jump.cuh, so iteration counts and
-//     hit iterations are those of the path-storing kernel (and of the reference on the same draws).
+//     hit iterations are those of the path-storing kernel (and of the reference on the same draws); a hit applies
+//     the jump with ONE predicated FFMA (x + base * 0 == x exactly, so skipping it is the same arithmetic).
 //   * the queue of pre-drawn (tau, c J) pairs is popped branch-free by bumping a shared-memory address on a hit.
 //     Whether a path ran out of queued jumps is checked once per group of 6 iterations (one Philox block of
 //     normals): the group runs speculatively from a saved (x, t, queue head); if the head left the filled part of
 //     the queue the group is replayed from the saved state with the per-iteration refill test (rare: a path needs
 //     more than `qdepth` jumps).  The Philox counters of normals and jumps are those of jump.cuh, so this kernel
 //     and the path-storing kernel simulate identical paths for the same seed.
+//   * phase 2 -- the num_steps % 6 last nominal iterations plus those forced by jumps -- runs in PAIRS (the two
+//     iterations that share one Box-Muller pair) with the `t < T` test between pairs: a warp stops within two
+//     iterations of its slowest lane instead of six (round 1: 2.3 masked groups of six per warp, 16 % of all
+//     instructions of the kernel).
 #pragma once
 #include "jump.cuh"
 
@@ -27,10 +36,12 @@ constexpr int kQueueSlack = kNormalsPerBlock;  // slots a speculative group may 
 #ifndef SDEMC_JUMP1D_MIN_BLOCKS
 #define SDEMC_JUMP1D_MIN_BLOCKS 3  // 80 registers, no spills in the step loop: measured 5% faster than 4 CTAs with spills
 #endif
-template <class C, bool EXACT>
+// EXACT: exact_jumps (:214-217).  TERM: the payoff reads the state at array index num_steps ('terminal', quirk Q1)
+// instead of the last state.  SAT: h0 <= 1, the dt >= 0 clamp rides on the subtraction (see above).
+template <class C, bool EXACT, bool TERM, bool SAT>
 __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
     jump1d_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys, const int qdepth,
-                  const DevPerPath pp, double* __restrict__ d_moments, void* __restrict__ d_ws) {
+                  const int nb_uncapped, const DevPerPath pp, double* __restrict__ d_moments, void* __restrict__ d_ws) {
   static_assert(C::DIM == 1 && C::M == 1 && !C::ASIAN, "1-D single-driver models only");
   constexpr int MARKS = C::MARKS;
   constexpr int G = kNormalsPerBlock;  // iterations per group
@@ -63,9 +74,9 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
     float tau_acc = queue_refill<MARKS, true>(qdepth, 0u, plo, phi, 0.0f);  // initial fill
     uint32_t q = q_base;
 
-    // one loop iteration.  CHECKED: refill test before the read (replay path); MASKED: the iteration only acts
-    // while t < T (phase 2), mirroring `while t < T` of the reference per path.
-    auto iteration = [&](float r2, float cs, auto checked, auto masked, int& k, float& x_at_n) {
+    // one loop iteration.  CHECKED: refill test before the read (replay path, phase 2); CAPPED: dt is capped at T
+    // (needed once t can come within h0 of T); returns whether the jump was hit.
+    auto iteration = [&](float r2, float cs, auto checked, auto capped) {
       if (decltype(checked)::value) {
         if (q >= q_end) {
           tau_acc = queue_refill<MARKS, true>(qdepth, chunk, plo, phi, tau_acc);
@@ -73,27 +84,23 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
           q = q_base;
         }
       }
-      const bool active = decltype(masked)::value ? (t < T && k < kcap) : true;
       const float2 e = lds_float2(q);  // (tau, c J)
-      const float dt = fmaxf(fminf(h0, fminf(e.x, T) - t), 0.0f);
+      const float m = decltype(capped)::value ? fminf(e.x, T) : e.x;
+      const float dt = SAT ? fminf(h0, __saturatef(m - t)) : fmaxf(fminf(h0, m - t), 0.0f);
       // sigma z sqrt(dt) = sqrt(sigma^2 (-2 ln u) dt) * (cos | sin): the Box-Muller root and sqrt(dt) are one MUFU
       const float g = fmaf(fast_sqrt(r2 * dt), cs, a * dt);
-      const float xn = GEO ? fmaf(x, g, x) : x + g;
+      float xn = GEO ? fmaf(x, g, x) : x + g;
       t += dt;
       // torch.isclose(tau, t, atol=1e-12) with its default rtol=1e-5 (:212,225), evaluated exactly as jump.cuh and
       // the reference do (t >= 0).  The one-FMA form t (1 + 1e-5) + 1e-12 >= tau used here in round 1 rounds its
       // threshold differently: about one path in 1e6 then hit a jump one iteration early -- or, for a jump 1e-5 T
       // after T, hit a jump the reference never applies (found by tests/test_gpu_fastpath.py).
-      bool hit = fabsf(e.x - t) <= fmaf(t, 1e-5f, 1e-12f);
-      if (decltype(masked)::value) hit = hit && active;
-      const float Jc = hit ? e.y : 0.0f;
-      if (GEO) x = fmaf(EXACT ? xn : x, Jc, xn);
-      else x = xn + Jc;
-      if (hit) q += q_stride;
-      if (decltype(masked)::value) {
-        k += active ? 1 : 0;
-        if (active && k == n) x_at_n = x;
+      const bool hit = fabsf(e.x - t) <= fmaf(t, 1e-5f, 1e-12f);
+      if (hit) {  // one predicated FFMA / FADD and the queue pop
+        xn = GEO ? fmaf(EXACT ? xn : x, e.y, xn) : xn + e.y;
+        q += q_stride;
       }
+      x = xn;
     };
     // one Philox block -> squared radii (sigma^2 folded in) and directions of 6 normals; normal 2j uses
     // (r2[j], cos), normal 2j+1 uses (r2[j], sin)
@@ -108,47 +115,60 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
         cs[2 * j + 1] = sn[j];
       }
     };
-
-    // phase 1: the first num_steps iterations can never reach T (each advances by at most T / num_steps): whole
-    // groups without the exit test, speculative on the queue.
-    int k = 0;
-    float x_at_n = x;
-    const int nb_full = n / G;
-    for (int b = 0; b < nb_full; ++b) {
+    // a full group of phase 1: speculative on the queue, replayed with the refill test if the head ran past it
+    auto phase1_group = [&](int b, auto capped) {
       float r2[3], cs[G];
       group_normals(b, r2, cs);
       const float xs = x, ts = t;
       const uint32_t qs = q;
 #pragma unroll
-      for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::false_type(), std::false_type(), k, x_at_n);
+      for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::false_type(), capped);
       if (q >= q_end) {  // ran out of queued jumps inside the group: replay it with the refill test
         x = xs;
         t = ts;
         q = qs;
         group_normals(b, r2, cs);  // recomputed rather than kept live across the speculative group
 #pragma unroll
-        for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::true_type(), std::false_type(), k, x_at_n);
+        for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::true_type(), std::true_type());
         if (q >= q_end) {  // the next group must start on a valid head
           tau_acc = queue_refill<MARKS, true>(qdepth, chunk, plo, phi, tau_acc);
           ++chunk;
           q = q_base;
         }
       }
-    }
-    k = nb_full * G;
-    if (k == n) x_at_n = x;
-    // phase 2: the remaining num_steps % 6 iterations and those forced by jumps, until t reaches T
-    for (int b = nb_full; t < T && k < kcap; ++b) {
+    };
+
+    // phase 1: the first num_steps iterations can never reach T (each advances by at most T / num_steps): whole
+    // groups without the exit test; the first nb_uncapped of them stay h0 away from T and skip the cap as well
+    const int nb_full = n / G;
+    int b = 0;
+    for (; b < nb_uncapped; ++b) phase1_group(b, std::false_type());
+    for (; b < nb_full; ++b) phase1_group(b, std::true_type());
+    int k = nb_full * G;
+    float x_at_n = x;
+    // phase 2: the remaining num_steps % 6 iterations and those forced by jumps, until t reaches T -- in pairs
+    while (t < T && k < kcap) {
       float r2[3], cs[G];
-      group_normals(b, r2, cs);
+      group_normals(b++, r2, cs);
 #pragma unroll
-      for (int sp = 0; sp < G; ++sp) iteration(r2[sp / 2], cs[sp], std::true_type(), std::true_type(), k, x_at_n);
+      for (int j = 0; j < 3; ++j) {
+        if (t < T && k < kcap) {
+          iteration(r2[j], cs[2 * j], std::true_type(), std::true_type());
+          ++k;
+          if (TERM && k == n) x_at_n = x;
+          if (t < T) {
+            iteration(r2[j], cs[2 * j + 1], std::true_type(), std::true_type());
+            ++k;
+            if (TERM && k == n) x_at_n = x;
+          }
+        }
+      }
     }
 
     float xp[kMaxDim];
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) xp[d] = 0.0f;
-    xp[0] = po.index_mode == SDEMC_INDEX_TERMINAL ? x_at_n : x;
+    xp[0] = TERM ? x_at_n : x;
     const float pay = eval_payoff<1>(po, xp);
     write_per_path<1>(pp, i, pay, k, xp);
     {

@@ -29,9 +29,9 @@ int run(const LaunchArgs& a) {
 }
 
 // moments-only fast path for 1-D single-driver models with queued (sparse) jumps: jump1d.cuh
-template <class C, bool EXACT>
-int run_1d(const LaunchArgs& a) {
-  auto kernel = jump1d_kernel<C, EXACT>;
+template <class C, bool EXACT, bool TERM, bool SAT>
+int run_1d_inst(const LaunchArgs& a) {
+  auto kernel = jump1d_kernel<C, EXACT, TERM, SAT>;
   const size_t smem = (size_t)(a.qdepth + kQueueSlack) * kBlock * sizeof(float2);
   // always opt in: the kernel also has ~17 KB of static shared memory, so the 48 KB default can be exceeded by
   // dynamic sizes below 48 KB
@@ -39,10 +39,22 @@ int run_1d(const LaunchArgs& a) {
   int grid = 0;
   int rc = pick_grid(kernel, smem, a.range.n_paths, &grid);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.qdepth, per_path_of_out(a.out),
-                                           a.d_moments, a.d_ws);
+  // groups of six iterations that end at least 1.5 h0 before T (t never exceeds its nominal grid point, up to the
+  // rounding of at most num_steps additions): dt needs no cap at T there (jump1d.cuh)
+  const int n = a.sde.num_steps;
+  int nb_uncapped = (int)std::floor(((double)n - 1.5) / kNormalsPerBlock);
+  nb_uncapped = std::max(0, std::min(nb_uncapped, n / kNormalsPerBlock));
+  kernel<<<grid, kBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.qdepth, nb_uncapped,
+                                           per_path_of_out(a.out), a.d_moments, a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
+}
+template <class C, bool EXACT>
+int run_1d(const LaunchArgs& a) {
+  const bool term = a.payoff.index_mode == SDEMC_INDEX_TERMINAL;
+  const bool sat = a.sde.h0 <= 1.0f;  // the dt >= 0 clamp as FADD.SAT needs h0 <= 1
+  if (term) return sat ? run_1d_inst<C, EXACT, true, true>(a) : run_1d_inst<C, EXACT, true, false>(a);
+  return sat ? run_1d_inst<C, EXACT, false, true>(a) : run_1d_inst<C, EXACT, false, false>(a);
 }
 
 // moments-only kernel for short paths with inline jumps: lanes are persistent workers (jump_flat.cuh)
