@@ -419,8 +419,7 @@ def main():
     mlmc_result = None
     if mlmc:
         tot_mean, tot_var, tot_iters, tot_n = 0.0, 0.0, 0.0, 0.0
-        for nl, m in zip(mlmc_trials, mom):
-            r = m.read()
+        for nl, r in zip(mlmc_trials, mom.read()):      # one (levels, 8) tensor: one read
             mean_l, se_l = E.mean_and_stderr(r["sum"], r["sumsq"], int(nl))
             tot_mean += mean_l
             tot_var += se_l * se_l
@@ -545,11 +544,11 @@ def main():
             out["value"] = value / world
             out["e2e"]["value"] = e2e / world
             out["e2e"]["call"] = "sde_mc_b200.mc_multilevel(trials, levels, solver, payoff, discounter)"
-            out["e2e"]["d2h_bytes_per_step"] = 64 * len(MLMC_LEVELS)
+            out["e2e"]["d2h_bytes_per_step"] = 64 * len(MLMC_LEVELS)     # ONE read of the (levels, 8) fp64 tensor
             out["gpu_launches"] = args.steps * len(MLMC_LEVELS)
             out["config"].update({"levels": MLMC_LEVELS, "eps": MLMC_EPS, "trials_per_level": [int(v) for v in mlmc_trials],
                                   "fine_path_steps_per_pass": paths, "exact_jumps": True,
-                                  "parallelism": "every level sharded over %d GPU(s), one 64-byte all-reduce per level" % world})
+                                  "parallelism": "every level sharded over %d GPU(s), ONE all-reduce of the (levels, 8) fp64 moments per pass" % world})
             out["roofline"]["achieved"] = OPS_PER_PATH_STEP["mlmc"] * out["value"] / 1e12 / world
             out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
             # `value` counts NOMINAL fine steps (a level-0 path is one step), but a jump-adapted path executes

@@ -14,7 +14,7 @@
  *   - the library keeps no mutable global state and reads no environment variables: every choice of kernel
  *     is a function of the structs below; the caller provides scratch (`d_workspace`)
  *   - all path arithmetic is fp32 like the reference (torch default dtype); the moment
- *     accumulators are fp64; the MLMC pair entry point also has an fp64-state variant
+ *     accumulators are fp64; the coupled MLMC pair also exists with fp64 state (sdemc_mlmc_pair_f64)
  *   - every struct the caller fills starts with `struct_size` = sizeof(that struct): an entry point handed a struct
  *     of another size (a binding written against another header) returns SDEMC_ERR_BAD_ARG instead of reading past
  *     it; sdemc_abi_layout() reports the sizes this build expects
@@ -141,12 +141,24 @@ typedef struct {
 
 /* Which paths, and where their noise comes from.  Philox4x32-10 keyed by `seed`, countered by the GLOBAL
  * path id, so results do not depend on grid shape or on how a range is split over GPUs. */
+/* A path range that lives in DEVICE memory, written by sdemc_plan_mc / sdemc_plan_mlmc (below) and read by the kernels
+ * of a later launch on the same stream: this is what lets "pilot run -> size the main run -> main run" (mc.py:418-440,
+ * mlmc.py:77-97) be queued as ONE submission without a host read in between. */
+typedef struct {
+  uint64_t path_lo;
+  uint64_t n_paths;
+} sdemc_dev_range;
+
 typedef struct {
   uint32_t struct_size; /* sizeof(sdemc_range) */
   uint32_t reserved;
   uint64_t seed;
   uint64_t path_lo;    /* first global path id of this call */
   uint64_t n_paths;    /* number of paths in this call */
+  /* NULL, or a device pointer: the kernels then take (path_lo, n_paths) from *d_range when they RUN, and the two host
+   * fields above only bound the grid (n_paths = 0: unknown, a full persistent grid).  Moments entry points only
+   * (sdemc_mc_moments, sdemc_mlmc_pair, sdemc_mc_cv), without injected noise or per-path outputs. */
+  const sdemc_dev_range* d_range;
 } sdemc_range;
 
 /* Injected noise for the deterministic-parity mode (replaces the three overridable sampling methods
@@ -219,7 +231,8 @@ int sdemc_device_info(int device, int* sm_count, int* clock_khz, uint64_t* mem_b
 /* Bytes of device scratch every entry point needs (per concurrent call). */
 uint64_t sdemc_workspace_bytes(void);
 /* Layout handshake: writes up to `n` of the sizes {sdemc_sde, sdemc_payoff, sdemc_range, sdemc_inject, sdemc_moments,
- * sdemc_paths_out, sdemc_mlp} this library was compiled with and returns how many there are (7).  A binding compares
+ * sdemc_paths_out, sdemc_mlp, sdemc_coeffs_f64, sdemc_inject_f64} this library was compiled with and returns how many
+ * there are (9).  A binding compares
  * them with its own struct definitions once at load time (sde_mc_b200/_lib.py does). */
 int sdemc_abi_layout(uint32_t* sizes, int n);
 
@@ -244,11 +257,41 @@ int sdemc_solve_paths(const sdemc_sde* sde, const sdemc_payoff* payoff /* may be
 
 /* H11/E4 fused: coupled fine/coarse jump-adapted (or uniform-grid) pair sharing increments and jumps,
  * accumulating D(T) (P(fine) - P(coarse)).  coarse == 0 runs the single level `fine` (mlmc.py:44-53).
- * use_fp64 != 0 keeps the path state in fp64 (the reference's jump MLMC only runs in fp64).
- * With inject != NULL and d_pair_out != NULL writes (n, 2, dim) terminal (fine, coarse) states instead. */
-int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse, int32_t use_fp64,
+ * fp32 path state (the reference's fp32 jump pair asserts, solvers.py:264: dt is clamped at 0 here instead).
+ * With inject != NULL and d_pair_out != NULL writes (n, 2, dim) fp32 terminal (fine, coarse) states instead. */
+int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse,
                     const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments,
-                    void* d_pair_out, void* d_workspace, void* stream);
+                    float* d_pair_out, void* d_workspace, void* stream);
+
+/* The same coupled jump-adapted pair with the path state, the coefficients, the marks and the payoff in fp64 -- the
+ * precision the reference's jump MLMC runs in (solvers.py:228-307 under torch.set_default_dtype(float64)).
+ * The float fields of sdemc_sde cannot carry 0.02 to 1e-12, so the coefficients come as doubles; sde supplies the
+ * model shape (family, dim, m, marks, max_jumps, exact_jumps).  Jump models only (marks != NONE), coarse >= 1. */
+typedef struct {
+  uint32_t struct_size; /* sizeof(sdemc_coeffs_f64) */
+  uint32_t reserved;
+  double T;
+  double x0[SDEMC_MAX_DIM];
+  double chol[SDEMC_MAX_DIM * SDEMC_MAX_DIM];
+  double a[SDEMC_MAX_DIM], b1[SDEMC_MAX_DIM], b2[SDEMC_MAX_DIM], c[SDEMC_MAX_DIM];
+  double rate;
+  double mark_p[12];    /* as sdemc_sde.mark_p */
+  double strike, transform_discount, aux, df; /* the payoff's real-valued fields (sdemc_payoff gives kind and log) */
+} sdemc_coeffs_f64;
+/* injected fp64 noise, layouts as sdemc_inject with K = outer iterations: d_z (n, K * fine/coarse, dim),
+ * d_zc (n, K * fine/coarse), d_jump_times (n, max_jumps), d_marks (n, K) */
+typedef struct {
+  uint32_t struct_size; /* sizeof(sdemc_inject_f64) */
+  int32_t K;
+  const double* d_z;
+  const double* d_zc;
+  const double* d_jump_times;
+  const double* d_marks;
+} sdemc_inject_f64;
+/* d_pair_out (may be NULL): (n, 2, dim) fp64 terminal (fine, coarse) states.  Moments are always accumulated. */
+int sdemc_mlmc_pair_f64(const sdemc_sde* sde, const sdemc_coeffs_f64* coeffs, const sdemc_payoff* payoff, int32_t fine,
+                        int32_t coarse, const sdemc_range* range, const sdemc_inject_f64* inject,
+                        sdemc_moments* d_moments, double* d_pair_out, void* d_workspace, void* stream);
 
 /* E5/E6/E7 fused: simulate + evaluate the control-variate MLPs f, g along each path on tensor cores and
  * accumulate gamma = payoff + sum f dW D + sum g D J - sum rate E[J] g D h  (varred.py:98-131).
@@ -256,6 +299,22 @@ int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fi
 int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rate, float jump_mean,
                 const sdemc_mlp* f, const sdemc_mlp* g, const sdemc_range* range, const sdemc_inject* inject,
                 sdemc_moments* d_moments, float* d_gamma_out /* (n) or NULL */, void* d_workspace, void* stream);
+
+/* N2: size a run from its pilot on the device.  d_pilot = the pilot's (all-reduced) moments; writes the trial count
+ *   N = ceil((1.96 se / eps)^2 pilot_trials)              find_num_trials mc.py:418-427 (se = standard error of the pilot)
+ * rounded up to a multiple of `multiple_of` (ceil_mult mc.py:459; 0 or 1 = none) and capped at max_trials (0 = no cap)
+ * to *d_trials_out, and rank `rank` of `world`'s contiguous share of the global path ids [path_base, path_base + N) to
+ * *d_range_out -- to be handed to a moments entry point as sdemc_range.d_range on the same stream. */
+int sdemc_plan_mc(const sdemc_moments* d_pilot, uint64_t pilot_trials, double eps, uint64_t multiple_of, uint64_t max_trials,
+                  uint64_t path_base, int32_t rank, int32_t world, sdemc_dev_range* d_range_out, uint64_t* d_trials_out,
+                  void* stream);
+/* The MLMC allocation of get_optimal_trials mlmc.py:77-97 from n_levels pilot moments (d_pilot[l], `pilot_trials` pairs
+ * each): N_l = ceil(1.96^2 / eps^2 sqrt(V_l h_l) sum_k sqrt(V_k / h_k)), h_l = T / d_levels[l] (device int32 array).
+ * Writes N_l to d_trials_out[l] and this rank's share of level l's path ids to d_ranges_out[l]; the levels take
+ * consecutive id ranges starting at path_base. */
+int sdemc_plan_mlmc(const sdemc_moments* d_pilot, int32_t n_levels, const int32_t* d_levels, uint64_t pilot_trials, double T,
+                    double eps, uint64_t max_trials, uint64_t path_base, int32_t rank, int32_t world,
+                    sdemc_dev_range* d_ranges_out, uint64_t* d_trials_out, void* stream);
 
 /* Test hook: the noise of `range`'s paths exactly as the kernels compute it from Philox (same device functions, same
  * fp32 / MUFU arithmetic), `count` values per path and array, row-major (n, count):

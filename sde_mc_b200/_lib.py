@@ -55,12 +55,13 @@ class SdemcPayoff(_Sized):
 
 
 class SdemcRange(_Sized):
-    """SdemcRange(seed, path_lo, n_paths)"""
+    """SdemcRange(seed, path_lo, n_paths[, d_range]); d_range: device pointer to a (path_lo, n_paths) pair of uint64
+    written by sdemc_plan_mc / sdemc_plan_mlmc -- the kernels then read their range when they run"""
     _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("seed", C.c_uint64), ("path_lo", C.c_uint64),
-                ("n_paths", C.c_uint64)]
+                ("n_paths", C.c_uint64), ("d_range", C.c_void_p)]
 
-    def __init__(self, seed=0, path_lo=0, n_paths=0):
-        super().__init__(0, seed, path_lo, n_paths)
+    def __init__(self, seed=0, path_lo=0, n_paths=0, d_range=None):
+        super().__init__(0, seed, path_lo, n_paths, d_range)
 
 
 class SdemcInject(_Sized):
@@ -93,6 +94,19 @@ class SdemcMlp(_Sized):
                 ("n_hidden_layers", C.c_int32)]
 
 
+class SdemcCoeffsF64(_Sized):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("T", C.c_double), ("x0", C.c_double * MAX_DIM),
+                ("chol", C.c_double * (MAX_DIM * MAX_DIM)), ("a", C.c_double * MAX_DIM), ("b1", C.c_double * MAX_DIM),
+                ("b2", C.c_double * MAX_DIM), ("c", C.c_double * MAX_DIM), ("rate", C.c_double),
+                ("mark_p", C.c_double * 12), ("strike", C.c_double), ("transform_discount", C.c_double),
+                ("aux", C.c_double), ("df", C.c_double)]
+
+
+class SdemcInjectF64(_Sized):
+    _fields_ = [("struct_size", C.c_uint32), ("K", C.c_int32), ("d_z", C.c_void_p), ("d_zc", C.c_void_p),
+                ("d_jump_times", C.c_void_p), ("d_marks", C.c_void_p)]
+
+
 MOMENT_FIELDS = ("sum", "sumsq", "sum_c", "sumsq_c", "sum_pc", "n", "iters", "reserved")
 NUM_MOMENTS = len(MOMENT_FIELDS)
 
@@ -105,14 +119,21 @@ _SIGNATURES = {
     "sdemc_abi_layout": (C.c_int, [C.POINTER(C.c_uint32), C.c_int]),
     "sdemc_mc_moments": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.POINTER(SdemcRange),
                                    C.POINTER(SdemcPathsOut), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdemc_plan_mc": (C.c_int, [C.c_void_p, C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdemc_plan_mlmc": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_uint64,
+                                  C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdemc_debug_draws": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcRange), C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "sdemc_eval_payoff": (C.c_int, [C.POINTER(SdemcPayoff), C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "sdemc_solve_paths": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.POINTER(SdemcRange),
                                     C.POINTER(SdemcInject), C.POINTER(SdemcPathsOut), C.c_void_p, C.c_void_p]),
-    "sdemc_mlmc_pair": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.c_int32, C.c_int32, C.c_int32,
+    "sdemc_mlmc_pair": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.c_int32, C.c_int32,
                                   C.POINTER(SdemcRange), C.POINTER(SdemcInject), C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    "sdemc_mlmc_pair_f64": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcCoeffsF64), C.POINTER(SdemcPayoff), C.c_int32,
+                                      C.c_int32, C.POINTER(SdemcRange), C.POINTER(SdemcInjectF64), C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "sdemc_mc_cv": (C.c_int, [C.POINTER(SdemcSde), C.POINTER(SdemcPayoff), C.c_float, C.c_float, C.POINTER(SdemcMlp),
                               C.POINTER(SdemcMlp), C.POINTER(SdemcRange), C.POINTER(SdemcInject), C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -141,8 +162,8 @@ def load():
         if lib.sdemc_version() != ABI_VERSION:
             raise SdemcError("%s speaks ABI version %d, this binding %d -- rebuild it (make -C sde_mc_b200/csrc)"
                              % (LIB_PATH, lib.sdemc_version(), ABI_VERSION))
-        theirs = (C.c_uint32 * 7)()
-        lib.sdemc_abi_layout(theirs, 7)
+        theirs = (C.c_uint32 * 9)()
+        lib.sdemc_abi_layout(theirs, 9)
         if list(theirs) != struct_sizes():
             raise SdemcError("struct layouts of %s %s differ from this binding's %s" % (LIB_PATH, list(theirs),
                                                                                       struct_sizes()))
@@ -156,7 +177,7 @@ ABI_VERSION = 4
 def struct_sizes():
     """sizes in the order of sdemc_abi_layout()"""
     return [C.sizeof(SdemcSde), C.sizeof(SdemcPayoff), C.sizeof(SdemcRange), C.sizeof(SdemcInject), 8 * NUM_MOMENTS,
-            C.sizeof(SdemcPathsOut), C.sizeof(SdemcMlp)]
+            C.sizeof(SdemcPathsOut), C.sizeof(SdemcMlp), C.sizeof(SdemcCoeffsF64), C.sizeof(SdemcInjectF64)]
 
 
 def load_abi_version():

@@ -61,7 +61,8 @@ def cholesky_rows(corr_matrix, dim):
         for i in range(dim):
             out[i * L.MAX_DIM + i] = 1.0
         return out
-    chol = torch.linalg.cholesky(torch.as_tensor(corr_matrix).detach().cpu().float()).double()
+    # in the dtype the reference would factor it in (solvers.py:33-36: the default dtype; fp64 only for the fp64 pair)
+    chol = torch.linalg.cholesky(torch.as_tensor(corr_matrix).detach().cpu().to(torch.get_default_dtype())).double()
     n = chol.shape[0]
     if n != dim:
         raise ValueError("correlation matrix is %dx%d for a %d-dimensional SDE" % (n, n, dim))

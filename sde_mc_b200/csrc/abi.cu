@@ -4,6 +4,7 @@
 
 #include "cv.cuh"
 #include "launch.cuh"
+#include "plan.cuh"
 
 namespace sdemc {
 
@@ -37,10 +38,11 @@ static int solve_common(const sdemc_sde* sde, const sdemc_payoff* payoff, const 
   if (!sized_or_null(payoff) || !sized_or_null(inject) || !sized_or_null(out)) return SDEMC_ERR_BAD_ARG;
   if (!store && (!d_moments || !d_ws || !payoff)) return SDEMC_ERR_BAD_ARG;
   if (store && !out) return SDEMC_ERR_BAD_ARG;
+  if (range->d_range && (store || inject || out)) return SDEMC_ERR_BAD_ARG;  // device-resident ranges: plain moments runs
   // moments kernels only report what a path contributed; trajectories are sdemc_solve_paths' business
   if (!store && out && (out->d_paths || out->d_left || out->d_times || out->d_jumps || out->d_normals || out->d_total_steps))
     return SDEMC_ERR_BAD_ARG;
-  if (range->n_paths == 0) return SDEMC_OK;
+  if (range->n_paths == 0 && !range->d_range) return SDEMC_OK;
   const bool jumps = sde->marks != SDEMC_MARKS_NONE;
   if (inject) {
     if (!inject->d_z || inject->K < 1) return SDEMC_ERR_BAD_ARG;
@@ -51,8 +53,7 @@ static int solve_common(const sdemc_sde* sde, const sdemc_payoff* payoff, const 
   LaunchArgs a;
   a.sde = to_dev(*sde, sde->num_steps);
   a.payoff = to_dev(payoff);
-  a.range.path_lo = range->path_lo;
-  a.range.n_paths = range->n_paths;
+  a.range = to_dev(*range);
   a.keys = make_philox_keys(range->seed);
   a.inject = to_dev(inject);
   a.use_inject = inject != nullptr;
@@ -126,11 +127,11 @@ int sdemc_device_info(int device, int* sm_count, int* clock_khz, uint64_t* mem_b
 uint64_t sdemc_workspace_bytes(void) { return kWorkspaceBytes; }
 
 int sdemc_abi_layout(uint32_t* sizes, int n) {
-  const uint32_t all[7] = {(uint32_t)sizeof(sdemc_sde),    (uint32_t)sizeof(sdemc_payoff),    (uint32_t)sizeof(sdemc_range),
-                           (uint32_t)sizeof(sdemc_inject), (uint32_t)sizeof(sdemc_moments),   (uint32_t)sizeof(sdemc_paths_out),
-                           (uint32_t)sizeof(sdemc_mlp)};
-  for (int i = 0; sizes && i < n && i < 7; ++i) sizes[i] = all[i];
-  return 7;
+  const uint32_t all[9] = {(uint32_t)sizeof(sdemc_sde),        (uint32_t)sizeof(sdemc_payoff),    (uint32_t)sizeof(sdemc_range),
+                           (uint32_t)sizeof(sdemc_inject),     (uint32_t)sizeof(sdemc_moments),   (uint32_t)sizeof(sdemc_paths_out),
+                           (uint32_t)sizeof(sdemc_mlp),        (uint32_t)sizeof(sdemc_coeffs_f64), (uint32_t)sizeof(sdemc_inject_f64)};
+  for (int i = 0; sizes && i < n && i < 9; ++i) sizes[i] = all[i];
+  return 9;
 }
 
 int sdemc_mc_moments(const sdemc_sde* sde, const sdemc_payoff* payoff, const sdemc_range* range,
@@ -139,16 +140,41 @@ int sdemc_mc_moments(const sdemc_sde* sde, const sdemc_payoff* payoff, const sde
 }
 
 
+int sdemc_plan_mc(const sdemc_moments* d_pilot, uint64_t pilot_trials, double eps, uint64_t multiple_of, uint64_t max_trials,
+                  uint64_t path_base, int32_t rank, int32_t world, sdemc_dev_range* d_range_out, uint64_t* d_trials_out,
+                  void* stream) {
+  if (!d_pilot || !d_range_out || !d_trials_out || pilot_trials < 2 || !(eps > 0.0) || world < 1 || rank < 0 || rank >= world)
+    return SDEMC_ERR_BAD_ARG;
+  plan_mc_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const double*>(d_pilot), (double)pilot_trials, eps, multiple_of, max_trials, path_base, rank, world,
+      reinterpret_cast<uint64_t*>(d_range_out), d_trials_out);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+
+int sdemc_plan_mlmc(const sdemc_moments* d_pilot, int32_t n_levels, const int32_t* d_levels, uint64_t pilot_trials, double T,
+                    double eps, uint64_t max_trials, uint64_t path_base, int32_t rank, int32_t world,
+                    sdemc_dev_range* d_ranges_out, uint64_t* d_trials_out, void* stream) {
+  if (!d_pilot || !d_levels || !d_ranges_out || !d_trials_out || n_levels < 1 || n_levels > SDEMC_MAX_LEVELS ||
+      pilot_trials < 2 || !(eps > 0.0) || !(T > 0.0) || world < 1 || rank < 0 || rank >= world)
+    return SDEMC_ERR_BAD_ARG;
+  plan_mlmc_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const double*>(d_pilot), n_levels, d_levels, (double)pilot_trials, T, eps, max_trials, path_base, rank,
+      world, reinterpret_cast<uint64_t*>(d_ranges_out), d_trials_out);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+
 int sdemc_debug_draws(const sdemc_sde* sde, const sdemc_range* range, int32_t kind, int32_t count, float* d_a,
                       float* d_b, float* d_c, void* stream) {
   if (!valid_sde(sde) || !sized(range) || kind < SDEMC_DRAWS_BROWNIAN || kind > SDEMC_DRAWS_PACKED || count < 1 || !d_a)
     return SDEMC_ERR_BAD_ARG;
   if (kind != SDEMC_DRAWS_BROWNIAN && (!d_b || sde->marks == SDEMC_MARKS_NONE)) return SDEMC_ERR_BAD_ARG;
   if (kind == SDEMC_DRAWS_PACKED && !d_c) return SDEMC_ERR_BAD_ARG;
-  if (range->n_paths == 0) return SDEMC_OK;
+  if (range->n_paths == 0 && !range->d_range) return SDEMC_OK;
   DevRange rg;
-  rg.path_lo = range->path_lo;
-  rg.n_paths = range->n_paths;
+  rg = to_dev(*range);
+  if (rg.dyn) return SDEMC_ERR_BAD_ARG;
   return launch_debug_draws(*sde, rg, make_philox_keys(range->seed), kind, count, d_a, d_b, d_c,
                             reinterpret_cast<cudaStream_t>(stream));
 }
@@ -178,13 +204,12 @@ int sdemc_solve_paths(const sdemc_sde* sde, const sdemc_payoff* payoff, const sd
 
 extern "C" {
 
-int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse, int32_t use_fp64,
-                    const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments, void* d_pair_out,
+int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse,
+                    const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments, float* d_pair_out,
                     void* d_workspace, void* stream) {
   if (!valid_sde(sde) || !sized(range) || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
   if (!sized_or_null(payoff) || !sized_or_null(inject)) return SDEMC_ERR_BAD_ARG;
   if (fine < 1 || coarse < 0) return SDEMC_ERR_BAD_ARG;
-  if (use_fp64) return SDEMC_ERR_UNSUPPORTED;  // fp64 path state: not built (the fp32 pair clamps dt instead of asserting)
   if (coarse == 0) {
     // single level (mlmc.py:44-53): the plain fused moments kernel on `fine` steps, payoff at the last state
     if (inject || d_pair_out || !payoff) return SDEMC_ERR_BAD_ARG;
@@ -195,7 +220,7 @@ int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fi
     return solve_common(&lvl, &po, range, nullptr, nullptr, d_moments, d_workspace, stream, false, /*prefer_packed=*/true);
   }
   if (fine % coarse != 0 || fine == coarse) return SDEMC_ERR_BAD_ARG;
-  if (range->n_paths == 0) return SDEMC_OK;
+  if (range->n_paths == 0 && !range->d_range) return SDEMC_OK;
   const bool jumps = sde->marks != SDEMC_MARKS_NONE;
   if (inject) {
     if (!inject->d_z || inject->K < 1) return SDEMC_ERR_BAD_ARG;
@@ -206,8 +231,7 @@ int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fi
   a.sde = to_dev(*sde, fine);
   a.payoff = to_dev(payoff);
   a.payoff.index_mode = SDEMC_INDEX_ADAPTED;
-  a.range.path_lo = range->path_lo;
-  a.range.n_paths = range->n_paths;
+  a.range = to_dev(*range);
   a.keys = make_philox_keys(range->seed);
   a.inject = to_dev(inject);
   a.use_inject = inject != nullptr;
@@ -218,7 +242,24 @@ int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fi
   a.d_ws = d_workspace;
   a.stream = reinterpret_cast<cudaStream_t>(stream);
   a.out = to_dev(nullptr, 0);
-  return launch_pair(*sde, a, fine, coarse, reinterpret_cast<float*>(d_pair_out));
+  return launch_pair(*sde, a, fine, coarse, d_pair_out);
+}
+
+int sdemc_mlmc_pair_f64(const sdemc_sde* sde, const sdemc_coeffs_f64* co, const sdemc_payoff* payoff, int32_t fine,
+                        int32_t coarse, const sdemc_range* range, const sdemc_inject_f64* inject, sdemc_moments* d_moments,
+                        double* d_pair_out, void* d_workspace, void* stream) {
+  if (!valid_sde(sde) || !sized(co) || !sized(range) || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
+  if (!sized_or_null(payoff) || !sized_or_null(inject)) return SDEMC_ERR_BAD_ARG;
+  if (fine < 1 || coarse < 1 || fine % coarse != 0 || fine == coarse) return SDEMC_ERR_BAD_ARG;
+  if (sde->marks == SDEMC_MARKS_NONE || sde->asian || sde->family == SDEMC_FAMILY_HESTON || sde->family == SDEMC_FAMILY_USER ||
+      sde->scheme != SDEMC_SCHEME_EULER)
+    return SDEMC_ERR_UNSUPPORTED;
+  if (inject && (!inject->d_z || !inject->d_jump_times || !inject->d_marks || inject->K < 1 || (sde->m == 2 && !inject->d_zc)))
+    return SDEMC_ERR_BAD_ARG;
+  if (range->d_range && inject) return SDEMC_ERR_BAD_ARG;
+  if (range->n_paths == 0 && !range->d_range) return SDEMC_OK;
+  return launch_pair_f64(*sde, *co, payoff, fine, coarse, to_dev(*range), make_philox_keys(range->seed), inject,
+                         reinterpret_cast<double*>(d_moments), d_pair_out, d_workspace, reinterpret_cast<cudaStream_t>(stream));
 }
 
 static bool mlp_ok(const sdemc_mlp* m) {
@@ -244,7 +285,7 @@ int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rat
   if (!sized_or_null(inject) || !sized_or_null(f) || !sized_or_null(g)) return SDEMC_ERR_BAD_ARG;
   const bool jumps = sde->marks != SDEMC_MARKS_NONE;
   if (!mlp_ok(f) || (jumps && !mlp_ok(g))) return SDEMC_ERR_UNSUPPORTED;
-  if (range->n_paths == 0) return SDEMC_OK;
+  if (range->n_paths == 0 && !range->d_range) return SDEMC_OK;
   if (inject) {
     if (!inject->d_z || inject->K < 1) return SDEMC_ERR_BAD_ARG;
     if (jumps && (!inject->d_jump_times || !inject->d_marks)) return SDEMC_ERR_BAD_ARG;
@@ -254,8 +295,7 @@ int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rat
   a.sde = to_dev(*sde, sde->num_steps);
   a.payoff = to_dev(payoff);
   a.payoff.index_mode = SDEMC_INDEX_ADAPTED;
-  a.range.path_lo = range->path_lo;
-  a.range.n_paths = range->n_paths;
+  a.range = to_dev(*range);
   a.keys = make_philox_keys(range->seed);
   a.inject = to_dev(inject);
   a.use_inject = inject != nullptr;

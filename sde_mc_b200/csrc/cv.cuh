@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
 
   const int n = s.num_steps;
   const int kcap = JUMPS ? (INJECT ? inj.K : 4 * (n + s.max_jumps) + 64) : n;
-  const uint64_t n_tiles = (rg.n_paths + kCvRows - 1) / kCvRows;
+  const uint64_t n_tiles = (range_n(rg) + kCvRows - 1) / kCvRows;
   Accum acc;
   acc.zero();
 
@@ -501,9 +501,9 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
     for (uint64_t pair = blockIdx.x; pair * kCvTiles < n_tiles; pair += gridDim.x) {
       // ---- state 0 of my path -> first-layer activation vectors of my tile --------------------------------------
       p.i = (pair * kCvTiles + mine) * kCvRows + row;
-      p.valid = p.i < rg.n_paths;
+      p.valid = p.i < range_n(rg);
       {
-        const uint64_t gp = rg.path_lo + p.i;
+        const uint64_t gp = range_lo(rg) + p.i;
         p.plo = (uint32_t)gp;
         p.phi = (uint32_t)(gp >> 32);
       }

@@ -66,19 +66,19 @@ __global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, S
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   // warp-uniform trip count: in STORE mode all 32 lanes stage their outputs in lock-step, so lanes past the end of
   // the range keep iterating (their rows are never written)
-  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < rg.n_paths; wbase += stride) {
+  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < range_n(rg); wbase += stride) {
     const uint64_t i = wbase + (threadIdx.x & 31);
-    if (!STORE && i >= rg.n_paths) break;
-    const bool valid = i < rg.n_paths;
-    const uint64_t gp = rg.path_lo + i;
+    if (!STORE && i >= range_n(rg)) break;
+    const bool valid = i < range_n(rg);
+    const uint64_t gp = range_lo(rg) + i;
     const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
     float x[kMaxDim];
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) x[d] = d < DIM ? s.x0[d] : 0.0f;
     if (STORE) {
       float* tiles = diff_store_smem + (threadIdx.x >> 5) * (2 * Writer::kFloats);
-      wpaths.init(tiles, out.paths, out.pitch_state, wbase, rg.n_paths);
-      wnorm.init(tiles + Writer::kFloats, out.normals, out.pitch_normals, wbase, rg.n_paths);
+      wpaths.init(tiles, out.paths, out.pitch_state, wbase, range_n(rg));
+      wnorm.init(tiles + Writer::kFloats, out.normals, out.pitch_normals, wbase, range_n(rg));
 #pragma unroll
       for (int d = 0; d < DIM; ++d) wpaths.append(x[d]);
     }

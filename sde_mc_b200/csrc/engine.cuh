@@ -47,7 +47,19 @@ struct DevPayoff {
 
 struct DevRange {
   uint64_t path_lo, n_paths;
+  const uint64_t* dyn;  // device-resident {path_lo, n_paths} overriding the two above (sdemc_range.d_range), or nullptr
 };
+// The range a moments kernel works on.  With `dyn` set it is read from device memory at run time: the launch was
+// queued before the range was known (pilot -> size the run -> run without a host read in between, mc.py:418-440,
+// mlmc.py:77-97).  Read where it is used (once per path) through a volatile load, so the values never occupy
+// registers across the step loops; without `dyn` these are the constant-bank reads they always were.
+__device__ __forceinline__ uint64_t range_dyn_word(const DevRange& rg, int w) {
+  uint64_t v;
+  asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(rg.dyn + w));
+  return v;
+}
+__device__ __forceinline__ uint64_t range_n(const DevRange& rg) { return rg.dyn ? range_dyn_word(rg, 1) : rg.n_paths; }
+__device__ __forceinline__ uint64_t range_lo(const DevRange& rg) { return rg.dyn ? range_dyn_word(rg, 0) : rg.path_lo; }
 
 struct DevInject {
   const float* z;

@@ -112,6 +112,17 @@ inline DevPayoff to_dev(const sdemc_payoff* p) {
   return d;
 }
 
+// sdemc_range -> DevRange.  With a device-resident range the host field n_paths is only an upper bound used to size
+// the grid (0 = unknown: a full persistent grid).
+inline DevRange to_dev(const sdemc_range& r) {
+  DevRange d;
+  d.path_lo = r.path_lo;
+  d.n_paths = r.n_paths;
+  d.dyn = reinterpret_cast<const uint64_t*>(r.d_range);
+  if (d.dyn && d.n_paths == 0) d.n_paths = ~0ull >> 1;
+  return d;
+}
+
 inline DevInject to_dev(const sdemc_inject* j) {
   DevInject d;
   std::memset(&d, 0, sizeof d);

@@ -342,11 +342,11 @@ __global__ void __launch_bounds__(256, jump_min_blocks<C, JSRC, STORE>()) jump_k
   const int n = s.num_steps;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   // warp-uniform trip count (see diffusion.cuh): STORE stages its outputs with all 32 lanes in lock-step
-  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < rg.n_paths; wbase += stride) {
+  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < range_n(rg); wbase += stride) {
     const uint64_t i = wbase + (threadIdx.x & 31);
-    if (!STORE && i >= rg.n_paths) break;
-    const bool valid = i < rg.n_paths;
-    const uint64_t gp = rg.path_lo + i;
+    if (!STORE && i >= range_n(rg)) break;
+    const bool valid = i < range_n(rg);
+    const uint64_t gp = range_lo(rg) + i;
     const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
     JumpState st;
 #pragma unroll
@@ -393,11 +393,11 @@ __global__ void __launch_bounds__(256, jump_min_blocks<C, JSRC, STORE>()) jump_k
     if (STORE) {
       // lock-step over the whole allocation: finished paths idle with dt = 0 exactly as in the reference,
       // where the loop runs until the slowest path of the batch is done (:182).
-      w_paths.init(store_tiles + 0 * Writer::kFloats, out.paths, out.pitch_state, wbase, rg.n_paths);
-      w_left.init(store_tiles + 1 * Writer::kFloats, out.left, out.pitch_state, wbase, rg.n_paths);
-      w_jumps.init(store_tiles + 2 * Writer::kFloats, out.jumps, out.pitch_state, wbase, rg.n_paths);
-      w_times.init(store_tiles + 3 * Writer::kFloats, out.times, out.pitch_times, wbase, rg.n_paths);
-      w_norm.init(store_tiles + 4 * Writer::kFloats, out.normals, out.pitch_normals, wbase, rg.n_paths);
+      w_paths.init(store_tiles + 0 * Writer::kFloats, out.paths, out.pitch_state, wbase, range_n(rg));
+      w_left.init(store_tiles + 1 * Writer::kFloats, out.left, out.pitch_state, wbase, range_n(rg));
+      w_jumps.init(store_tiles + 2 * Writer::kFloats, out.jumps, out.pitch_state, wbase, range_n(rg));
+      w_times.init(store_tiles + 3 * Writer::kFloats, out.times, out.pitch_times, wbase, range_n(rg));
+      w_norm.init(store_tiles + 4 * Writer::kFloats, out.normals, out.pitch_normals, wbase, range_n(rg));
 #pragma unroll
       for (int d = 0; d < DIM; ++d) {
         w_paths.append(st.x[d]);

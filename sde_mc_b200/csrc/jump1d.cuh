@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(256, SDEMC_JUMP1D_MIN_BLOCKS)
 #pragma unroll
   for (int m = 0; m < kNumMoments - 1; ++m) acc_sh[m][threadIdx.x] = 0.0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
-    const uint64_t gp = rg.path_lo + i;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < range_n(rg); i += stride) {
+    const uint64_t gp = range_lo(rg) + i;
     const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
     float x = s.x0[0], t = 0.0f;
     uint32_t chunk = 1;

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256, 3)
   const int kcap = 4 * (n + s.max_jumps) + 64;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = i < rg.n_paths;
+  bool live = i < range_n(rg);
 
   JumpState st;
   Src src;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256, 3)
   int b = 0;          // group index inside the current path
   float xs[kMaxDim];  // state at array index num_steps ('terminal' payoff index)
   auto start_path = [&](uint64_t idx) {
-    const uint64_t gp = rg.path_lo + idx;
+    const uint64_t gp = range_lo(rg) + idx;
     plo = (uint32_t)gp;
     phi = (uint32_t)(gp >> 32);
 #pragma unroll
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256, 3)
       acc.add(pay, po.df * st.x[0] - s.x0[0], st.k);
       write_per_path<DIM>(pp, i, pay, st.k, xp);
       i += stride;
-      live = i < rg.n_paths;
+      live = i < range_n(rg);
       if (live) start_path(i);
     }
   }
@@ -158,14 +158,14 @@ __global__ void __launch_bounds__(256, 3)
   const int kcap = 4 * (n + s.max_jumps) + 64;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = i < rg.n_paths;
+  bool live = i < range_n(rg);
 
   JumpState st;
   Src src;
   uint32_t plo = 0, phi = 0;
   float x_at_n = 0.0f;  // state at array index num_steps ('terminal' payoff index)
   auto start_path = [&](uint64_t idx) {
-    const uint64_t gp = rg.path_lo + idx;
+    const uint64_t gp = range_lo(rg) + idx;
     plo = (uint32_t)gp;
     phi = (uint32_t)(gp >> 32);
 #pragma unroll
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 3)
       acc.add(pay, po.df * st.x[0] - s.x0[0], st.k);
       write_per_path<1>(pp, i, pay, st.k, xp);
       i += stride;
-      live = i < rg.n_paths;
+      live = i < range_n(rg);
       if (live) start_path(i);
     }
   }

@@ -27,6 +27,9 @@ int launch_jump(const sdemc_sde& s, const LaunchArgs& a);
 int launch_pair(const sdemc_sde& s, const LaunchArgs& a, int fine, int coarse, float* d_terminal);
 int launch_debug_draws(const sdemc_sde& s, const DevRange& rg, const PhiloxKeys& keys, int kind, int count, float* a,
                        float* b, float* c, cudaStream_t stream);
+int launch_pair_f64(const sdemc_sde& s, const sdemc_coeffs_f64& co, const sdemc_payoff* payoff, int fine, int coarse,
+                    const DevRange& rg, const PhiloxKeys& keys, const sdemc_inject_f64* inject, double* d_moments,
+                    double* d_terminal, void* d_ws, cudaStream_t stream);
 struct DevMlp;
 struct DevCv;
 int launch_cv(const sdemc_sde& s, const LaunchArgs& a, const DevMlp& f, const DevMlp& g, const DevCv& cv);

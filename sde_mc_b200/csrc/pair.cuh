@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256) jump_pair_kernel(const DevSde s, const De
   Accum acc;
   acc.zero();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
-    const uint64_t gp = rg.path_lo + i;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < range_n(rg); i += stride) {
+    const uint64_t gp = range_lo(rg) + i;
     PairPath<C, INJECT> p;
     p.start(s, inj, i, (uint32_t)gp, (uint32_t)(gp >> 32));
     while (p.tf < s.T && p.k < kcap) pair_iteration<C, INJECT>(s, keys, inj, p, i, factor, hf0, hc0);   // :254
@@ -195,10 +195,10 @@ __global__ void __launch_bounds__(256) jump_pair_flat_kernel(const DevSde s, con
   acc.zero();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = i < rg.n_paths;
+  bool live = i < range_n(rg);
   PairPath<C, false> p;
   {
-    const uint64_t gp = rg.path_lo + (live ? i : 0);
+    const uint64_t gp = range_lo(rg) + (live ? i : 0);
     p.start(s, no_inject, i, (uint32_t)gp, (uint32_t)(gp >> 32));
   }
   while (live) {
@@ -210,9 +210,9 @@ __global__ void __launch_bounds__(256) jump_pair_flat_kernel(const DevSde s, con
       const float diff = eval_payoff<DIM>(po, p.xf) - eval_payoff<DIM>(po, p.xc);
       acc.add(diff, 0.0f, p.k * factor);
       i += stride;
-      live = i < rg.n_paths;
+      live = i < range_n(rg);
       if (live) {
-        const uint64_t gp = rg.path_lo + i;
+        const uint64_t gp = range_lo(rg) + i;
         p.start(s, no_inject, i, (uint32_t)gp, (uint32_t)(gp >> 32));
       }
     }
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(256) diffusion_pair_kernel(const DevSde s, con
   Accum acc;
   acc.zero();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rg.n_paths; i += stride) {
-    const uint64_t gp = rg.path_lo + i;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < range_n(rg); i += stride) {
+    const uint64_t gp = range_lo(rg) + i;
     const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
     float xf[kMaxDim], xc[kMaxDim];
 #pragma unroll

@@ -277,10 +277,19 @@ def find_num_trials_terminal_cv(problem, eps, init_trials, bs):
 
 
 def run_mc(problem, eps, bs=1e5, init_trials=1e5):
-    """Plain MC to tolerance (mc.py:437-440)."""
-    trials = find_num_trials(problem, eps, None, init_trials, bs)
+    """Plain MC to tolerance (mc.py:437-440): pilot -> trial count -> main run.  With a built-in payoff the three
+    stages are one submission (E.run_to_tolerance): the count is computed on the device from the pilot's moments and
+    the main kernel reads its path range from device memory; the host reads (moments, N) once at the end."""
     payoff_time = 'adapted' if problem.solver.has_jumps else 'terminal'
-    return mc_simple(trials, problem.solver, problem.payoff, problem.discounter, bs=bs, payoff_time=payoff_time)
+    if _spec.payoff_kernel_spec(problem.payoff) is None:
+        trials = find_num_trials(problem, eps, None, init_trials, bs)
+        return mc_simple(trials, problem.solver, problem.payoff, problem.discounter, bs=bs, payoff_time=payoff_time)
+    start = time.time()
+    discounter = problem.discounter if problem.discounter is not None else ConstantShortRate(r=0.0)
+    mom, trials = E.run_to_tolerance(problem.solver, problem.payoff, discounter, eps, init_trials,
+                                     _index_mode(payoff_time))
+    mean, stderr = E.mean_and_stderr(mom['sum'], mom['sumsq'], trials)
+    return MCStatistics(mean, stderr, time.time() - start, trials)
 
 
 def run_cv_mc(problem, models, opt, eps, train_size, step_factor=30, sim_bs=1e5, train_bs=1e3, nn_bs=1e3, epochs=10,
@@ -299,8 +308,19 @@ def run_cv_mc(problem, models, opt, eps, train_size, step_factor=30, sim_bs=1e5,
     train_time = time.time() - t0
     gc.collect()
     problem.solver.num_steps = steps
-    trials = ceil_mult(find_num_trials(problem, eps, models, init_trials, sim_bs), nn_bs)
-    stats = mc_apply_cvs(models, problem.solver, trials, problem.payoff, problem.discounter, sim_bs, nn_bs)
+    if (fused_cv_supported(models, problem.solver, 0) and isinstance(problem.discounter, ConstantShortRate)
+            and _spec.payoff_kernel_spec(problem.payoff) is not None):
+        # pilot with the control variates -> ceil_mult(N, nn_bs) on the device -> main run: one submission
+        t1 = time.time()
+        mom, trials = E.run_to_tolerance(
+            problem.solver, problem.payoff, problem.discounter, eps, init_trials, L.INDEX_ADAPTED, multiple_of=int(nn_bs),
+            launch=lambda n, dev_range=None: mc_cv_fused(models, problem.solver, n, problem.payoff, problem.discounter,
+                                                         dev_range=dev_range))
+        mean, stderr = E.mean_and_stderr(mom['sum'], mom['sumsq'], trials)
+        stats = MCStatistics(mean, stderr, time.time() - t1, trials)
+    else:
+        trials = ceil_mult(find_num_trials(problem, eps, models, init_trials, sim_bs), nn_bs)
+        stats = mc_apply_cvs(models, problem.solver, trials, problem.payoff, problem.discounter, sim_bs, nn_bs)
     test_time = stats.time_elapsed
     stats.time_elapsed += train_time
     return stats, train_time, test_time

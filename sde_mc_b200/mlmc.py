@@ -26,87 +26,177 @@ def _pair_lib(solver):
     return L.load()
 
 
-def _level_moments(solver, payoff, discounter, trials, fine, coarse):
-    """moments of D(T) (P(fine) - P(coarse)) over `trials` coupled pairs (coarse == 0: single level)."""
-    trials = int(trials)
+def _wants_fp64(solver):
+    """The reference's jump MLMC runs under torch.set_default_dtype(torch.float64) (its fp32 pair asserts,
+    solvers.py:264).  The same switch selects the fp64-state pair kernel here (sdemc_mlmc_pair_f64); the fp32 pair
+    kernel -- dt clamped at 0 instead of the assert -- serves the default dtype."""
+    return torch.get_default_dtype() == torch.float64 and bool(solver.has_jumps)
+
+
+def _coeffs_f64(solver, payoff=None, df=1.0):
+    """the model's coefficients as doubles (KernelSpec holds python floats; sdemc_sde narrows them to fp32)"""
+    spec = _spec.spec_of(solver.sde)
+    c = L.SdemcCoeffsF64()
+    c.T = float(solver.time_interval)
+    for i in range(L.MAX_DIM):
+        c.x0[i], c.a[i], c.b1[i], c.b2[i], c.c[i] = spec.x0[i], spec.a[i], spec.b1[i], spec.b2[i], spec.c[i]
+    for i in range(L.MAX_DIM * L.MAX_DIM):
+        c.chol[i] = spec.chol[i]
+    c.rate = spec.rate
+    for i in range(12):
+        c.mark_p[i] = spec.mark_p[i]
+    c.strike, c.transform_discount, c.aux, c.df = 0.0, 1.0, 1.0, float(df)
+    if payoff is not None:
+        _, strike, aux = _spec.payoff_kernel_spec(payoff)()
+        c.strike, c.transform_discount, c.aux = float(strike), float(payoff.discount), float(aux)
+    return c
+
+
+def _level_moments(solver, payoff, discounter, trials, fine, coarse, buf=None, dev_range=None, reduce=True):
+    """moments of D(T) (P(fine) - P(coarse)) over `trials` coupled pairs (coarse == 0: single level), accumulated
+    into `buf` (a row of the estimator's (levels, 8) tensor) or a fresh Moments.  dev_range = (DeviceRange, row): the
+    kernel reads this level's path range from device memory (run_mlmc)."""
     dev = solver._compute_device()
     lib = _pair_lib(solver)
     rank, size = E.world()
-    lo = solver._take_paths(trials)
-    off, cnt = E.shard(trials, rank, size)
-    po = _spec.payoff_struct(payoff, float(discounter(solver.time_interval)), L.INDEX_ADAPTED)
+    if dev_range is not None:
+        lo, off, cnt = 0, 0, int(trials or 0)
+        d_range = dev_range[0].row_ptr(dev_range[1])
+    else:
+        trials = int(trials)
+        lo = solver._take_paths(trials)
+        off, cnt = E.shard(trials, rank, size)
+        d_range = None
+    df = float(discounter(solver.time_interval))
+    po = _spec.payoff_struct(payoff, df, L.INDEX_ADAPTED)
     sde = solver._sde_struct(fine)
     with torch.cuda.device(dev):
-        mom = E.Moments(dev)
-        rng = L.SdemcRange(int(solver.seed), lo + off, cnt)
-        L.check(lib.sdemc_mlmc_pair(sde, po, int(fine), int(coarse), 0, rng, None, L.ptr(mom.buf), None,
-                                    L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
-        mom.all_reduce()
+        mom = E.Moments(dev, buf)
+        rng = L.SdemcRange(int(solver.seed), lo + off, cnt, d_range)
+        if _wants_fp64(solver) and coarse > 0:
+            L.check(lib.sdemc_mlmc_pair_f64(sde, _coeffs_f64(solver, payoff, df), po, int(fine), int(coarse), rng, None,
+                                            L.ptr(mom.buf), None, L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+        else:
+            L.check(lib.sdemc_mlmc_pair(sde, po, int(fine), int(coarse), rng, None, L.ptr(mom.buf), None,
+                                        L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+        if reduce:
+            mom.all_reduce()
     return mom
 
 
 _level_streams = {}
 
 
-def _all_levels(solver, payoff, discounter, trials, levels):
-    """Queue one launch per level and return their Moments.  The levels are independent, so each goes to a stream of
-    its own (forked from and joined back into the current stream): level 0 fills the GPU first, the small fine levels
-    -- a wave or two of long serial paths each -- then overlap instead of running their tails one after the other.
-    SDEMC_MLMC_STREAMS=0 keeps everything on the current stream."""
+class LevelMoments:
+    """The fp64 moments of all levels of one MLMC estimator: ONE (levels, 8) device tensor, so the estimator costs
+    one all-reduce (8 x 64 bytes) and one device -> host read, however many levels it has."""
+
+    def __init__(self, device, n_levels):
+        self.buf = torch.zeros((n_levels, L.NUM_MOMENTS), dtype=torch.float64, device=device)
+
+    def all_reduce(self):
+        if E.world()[1] > 1:
+            torch.distributed.all_reduce(self.buf, op=torch.distributed.ReduceOp.SUM)
+        return self
+
+    def read(self):
+        return [dict(zip(L.MOMENT_FIELDS, row)) for row in self.buf.tolist()]
+
+
+def _all_levels(solver, payoff, discounter, trials, levels, plan=None):
+    """Queue one launch per level into the rows of one LevelMoments and all-reduce it ONCE.  The levels are
+    independent, so each goes to a stream of its own (forked from and joined back into the current stream): level 0
+    fills the GPU first, the small fine levels -- a wave or two of long serial paths each -- then overlap instead of
+    running their tails one after the other.  SDEMC_MLMC_STREAMS=0 keeps everything on the current stream.
+    plan: an E.DeviceRange with one row per level (run_mlmc) -- the kernels read their ranges from device memory."""
     import os
     trials = [trials] * len(levels) if not isinstance(trials, (list, tuple)) else trials
     dev = solver._compute_device()
     coarse = [0] + list(levels[:-1])
-    if os.environ.get("SDEMC_MLMC_STREAMS", "1") == "0" or len(levels) < 2:
-        return [_level_moments(solver, payoff, discounter, n, f, c) for n, f, c in zip(trials, levels, coarse)]
     with torch.cuda.device(dev):
+        out = LevelMoments(dev, len(levels))
+        rows = [out.buf[i] for i in range(len(levels))]
+        dr = [(plan, i) if plan is not None else None for i in range(len(levels))]
+        if os.environ.get("SDEMC_MLMC_STREAMS", "1") == "0" or len(levels) < 2:
+            for n, f, c, row, d in zip(trials, levels, coarse, rows, dr):
+                _level_moments(solver, payoff, discounter, n, f, c, row, d, reduce=False)
+            return out.all_reduce()
         pool = _level_streams.setdefault(dev, [])
         while len(pool) < len(levels):
             pool.append(torch.cuda.Stream(device=dev))
         cur = torch.cuda.current_stream(dev)
         fork = torch.cuda.Event()
         fork.record(cur)
-        pending = []
-        for side, n, f, c in zip(pool, trials, levels, coarse):
+        for side, n, f, c, row, d in zip(pool, trials, levels, coarse, rows, dr):
             side.wait_event(fork)
             with torch.cuda.stream(side):
-                mom = _level_moments(solver, payoff, discounter, n, f, c)
-                mom.buf.record_stream(cur)       # read (and possibly freed) on the caller's stream
+                _level_moments(solver, payoff, discounter, n, f, c, row, d, reduce=False)
             join = torch.cuda.Event()
             join.record(side)
             cur.wait_event(join)
-            pending.append(mom)
-    return pending
+        out.buf.record_stream(cur)
+        return out.all_reduce()
+
+
+def _combine(levels_read, trials):
+    total_mean, total_var = 0.0, 0.0
+    for n, m in zip(trials, levels_read):
+        mean, var = mc_estimates(m['sum'], m['sumsq'], int(n))
+        total_mean += mean
+        total_var += var / int(n)
+    return total_mean, total_var ** 0.5
 
 
 def mc_multilevel(trials, levels, solver, payoff, discounter, bs=None):
     """MLMC estimate  sum_l E[P_l - P_{l-1}]  with trials[l] coupled pairs on level l (mlmc.py:7-74).
-    `bs` is accepted for compatibility; nothing is stored so no batching is needed."""
+    `bs` is accepted for compatibility; nothing is stored so no batching is needed.  One launch per level, ONE
+    all-reduce and ONE host read for the whole estimator."""
     start = time.time()
     pending = _all_levels(solver, payoff, discounter, [int(n) for n in trials], levels)
-    total_mean, total_var = 0.0, 0.0
-    for n, mom in zip(trials, pending):          # one host read per level, after all launches are queued
-        m = mom.read()
-        mean, var = mc_estimates(m['sum'], m['sumsq'], int(n))
-        total_mean += mean
-        total_var += var / int(n)
-    return MCStatistics(total_mean, total_var ** 0.5, time.time() - start, trials[-1])
+    mean, stderr = _combine(pending.read(), trials)
+    return MCStatistics(mean, stderr, time.time() - start, trials[-1])
 
 
 def get_optimal_trials(trials, levels, epsilon, solver, payoff, discounter):
     """Pilot of `trials` pairs per level -> N_l = ceil(1.96^2/eps^2 sqrt(V_l h_l) sum_k sqrt(V_k / h_k))
     (mlmc.py:77-97; eps is a 95% half-width)."""
     pending = _all_levels(solver, payoff, discounter, [int(trials)] * len(levels), levels)
-    variances = []
-    for mom in pending:
-        m = mom.read()
-        variances.append(mc_estimates(m['sum'], m['sumsq'], int(trials))[1])
+    variances = [mc_estimates(m['sum'], m['sumsq'], int(trials))[1] for m in pending.read()]
     variances = torch.tensor(variances, dtype=torch.float64)
     step_sizes = solver.time_interval / torch.tensor(levels, dtype=torch.float64)
     solver.num_steps = levels[0]                  # the reference leaves the solver on the coarsest level (:83)
     total = (variances / step_sizes).sqrt().sum()
     optimal = (1.96 ** 2 / (epsilon * epsilon)) * (variances * step_sizes).sqrt() * total
     return optimal.ceil().long().tolist()
+
+
+def run_mlmc(levels, epsilon, solver, payoff, discounter, pilot_trials=10 ** 5, max_trials=0):
+    """MLMC to tolerance as ONE submission (extension; the reference offers the two halves get_optimal_trials and
+    mc_multilevel, mlmc.py:7-97, with a host round trip between them): pilot of `pilot_trials` pairs per level -> one
+    all-reduce -> the allocation formula on the device (sdemc_plan_mlmc) -> the main run of every level, whose
+    kernels read their path ranges from device memory -> one all-reduce -> one host read of (moments, N_l).
+    Returns (MCStatistics, trials per level)."""
+    start = time.time()
+    dev = solver._compute_device()
+    rank, size = E.world()
+    pilot_trials = int(pilot_trials)
+    pilot = _all_levels(solver, payoff, discounter, [pilot_trials] * len(levels), levels)
+    with torch.cuda.device(dev):
+        plan = E.DeviceRange(dev, len(levels))
+        d_levels = torch.tensor([int(l) for l in levels], dtype=torch.int32, device=dev)
+        L.check(L.load().sdemc_plan_mlmc(L.ptr(pilot.buf), len(levels), L.ptr(d_levels), pilot_trials,
+                                         float(solver.time_interval), float(epsilon), int(max_trials),
+                                         int(solver._next_path), rank, size, L.ptr(plan.ranges), L.ptr(plan.trials),
+                                         L.stream_ptr(dev)))
+        main = _all_levels(solver, payoff, discounter, [0] * len(levels), levels, plan=plan)
+        packed = torch.cat([main.buf.reshape(-1), plan.trials.double()]).tolist()        # the one host read
+    n_lv = len(levels)
+    rows = [dict(zip(L.MOMENT_FIELDS, packed[i * L.NUM_MOMENTS:(i + 1) * L.NUM_MOMENTS])) for i in range(n_lv)]
+    trials = [int(v) for v in packed[n_lv * L.NUM_MOMENTS:]]
+    solver._take_paths(sum(trials))
+    solver.num_steps = levels[0]
+    mean, stderr = _combine(rows, trials)
+    return MCStatistics(mean, stderr, time.time() - start, trials[-1]), trials
 
 
 def mlmc_bs_from_trials(trials, levels, max_mem=5 * 10 ** 8, dim=1, max_jumps=0):
@@ -121,23 +211,32 @@ def _pair_terminals(solver, bs, levels, inject):
     lib = _pair_lib(solver)
     d = solver.sde.dim
     sde = solver._sde_struct(fine)
+    use64 = _wants_fp64(solver)
+    dt = torch.float64 if use64 else torch.float32
     keep = []
+
+    def as_dev(a):
+        return None if a is None else torch.as_tensor(a).to(device=dev, dtype=dt).contiguous()
+
     with torch.cuda.device(dev):
-        out = torch.empty((bs, 2, d), device=dev, dtype=torch.float32)
+        out = torch.empty((bs, 2, d), device=dev, dtype=dt)
         inj = None
         if inject is not None:
-            from .solvers import _as_dev_f32
-            z = _as_dev_f32(inject['z'], dev)
-            zc = _as_dev_f32(inject.get('zc'), dev)
-            jt = _as_dev_f32(inject.get('jump_times'), dev)
-            mk = _as_dev_f32(inject.get('marks'), dev)
+            z, zc, jt, mk = (as_dev(inject.get(k)) for k in ('z', 'zc', 'jump_times', 'marks'))
             keep += [z, zc, jt, mk]
             K = int(mk.shape[1]) if mk is not None else coarse
-            inj = L.SdemcInject(L.ptr(z), L.ptr(zc), L.ptr(jt), L.ptr(mk), K)
+            if use64:
+                inj = L.SdemcInjectF64(K, L.ptr(z), L.ptr(zc), L.ptr(jt), L.ptr(mk))
+            else:
+                inj = L.SdemcInject(L.ptr(z), L.ptr(zc), L.ptr(jt), L.ptr(mk), K)
         mom = E.Moments(dev)
         rng = L.SdemcRange(int(solver.seed), solver._take_paths(bs), bs)
-        L.check(lib.sdemc_mlmc_pair(sde, None, fine, coarse, 0, rng, inj, L.ptr(mom.buf), L.ptr(out),
-                                    L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+        if use64:
+            L.check(lib.sdemc_mlmc_pair_f64(sde, _coeffs_f64(solver), None, fine, coarse, rng, inj, L.ptr(mom.buf),
+                                            L.ptr(out), L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+        else:
+            L.check(lib.sdemc_mlmc_pair(sde, None, fine, coarse, rng, inj, L.ptr(mom.buf), L.ptr(out),
+                                        L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
     return solver._to_user_device(out)
 
 
@@ -145,7 +244,7 @@ def _pair_paths_jump(solver, bs, levels, inject):
     """((paths_fine, paths_coarse), None) where only the LAST index is meaningful -- the estimators read
     paths[:, -1] only (mlmc.py:64-65); shape (bs, 2, dim): index 0 = initial value, -1 = terminal state."""
     term = _pair_terminals(solver, bs, levels, inject)
-    x0 = solver.sde.init_value.to(term.device).unsqueeze(0).repeat(bs, 1)
+    x0 = solver.sde.init_value.to(device=term.device, dtype=term.dtype).unsqueeze(0).repeat(bs, 1)
     pf = torch.stack([x0, term[:, 0]], dim=1)
     pc = torch.stack([x0, term[:, 1]], dim=1)
     return (pf, pc), None

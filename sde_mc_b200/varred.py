@@ -201,8 +201,9 @@ def fused_cv_supported(models, solver, tol=0):
     return all(_export_mlp(n, 'cpu', keep) is not None for n in nets)
 
 
-def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_out=False):
-    """One launch: jump-adapted (or uniform) Euler + f/g MLPs on tensor cores + gamma + moments (sdemc_mc_cv)."""
+def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_out=False, dev_range=None):
+    """One launch: jump-adapted (or uniform) Euler + f/g MLPs on tensor cores + gamma + moments (sdemc_mc_cv).
+    dev_range: an _engine.DeviceRange -- the kernel reads its path range from device memory (run_cv_mc)."""
     trials = int(trials)
     dev = solver._compute_device()
     lib = L.load()
@@ -212,8 +213,11 @@ def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_o
         f = _export_mlp(nets[0], dev, keep)
         g = _export_mlp(nets[1], dev, keep) if solver.has_jumps else None
         rank, size = E.world()
-        lo = solver._take_paths(trials)
-        off, cnt = E.shard(trials, rank, size) if inject is None else (0, trials)
+        if dev_range is not None:
+            lo, off, cnt = 0, 0, trials
+        else:
+            lo = solver._take_paths(trials)
+            off, cnt = E.shard(trials, rank, size) if inject is None else (0, trials)
         df = float(discounter(solver.time_interval))
         po = _spec.payoff_struct(payoff, df, L.INDEX_ADAPTED)
         sde = solver._sde_struct()
@@ -228,7 +232,7 @@ def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_o
             mk = _as_dev_f32(inject.get('marks'), dev)
             keep += [z, jt, mk]
             inj = L.SdemcInject(L.ptr(z), None, L.ptr(jt), L.ptr(mk), int(z.shape[1]), int(inject.get('total_steps', 0)))
-        rng = L.SdemcRange(int(solver.seed), lo + off, cnt)
+        rng = L.SdemcRange(int(solver.seed), lo + off, cnt, dev_range.row_ptr() if dev_range is not None else None)
         L.check(lib.sdemc_mc_cv(sde, po, float(discounter.r), jm, f, g, rng, inj, L.ptr(mom.buf), L.ptr(gam),
                                 L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
         if inject is None:

@@ -218,7 +218,8 @@ def test_library_exports_every_declared_symbol():
 
 
 _C_NAMES = {"SdemcSde": "sdemc_sde", "SdemcPayoff": "sdemc_payoff", "SdemcRange": "sdemc_range",
-            "SdemcInject": "sdemc_inject", "SdemcPathsOut": "sdemc_paths_out", "SdemcMlp": "sdemc_mlp"}
+            "SdemcInject": "sdemc_inject", "SdemcPathsOut": "sdemc_paths_out", "SdemcMlp": "sdemc_mlp",
+            "SdemcCoeffsF64": "sdemc_coeffs_f64", "SdemcInjectF64": "sdemc_inject_f64"}
 
 
 def test_struct_layouts_match_the_header():
@@ -248,11 +249,12 @@ def test_struct_layouts_match_the_header():
     assert theirs["sdemc_moments"] == 8 * L.NUM_MOMENTS
     assert theirs["version"] == L.ABI_VERSION
     lib = L.load()
-    sizes = (ctypes.c_uint32 * 7)()
-    assert lib.sdemc_abi_layout(sizes, 7) == 7
+    sizes = (ctypes.c_uint32 * 9)()
+    assert lib.sdemc_abi_layout(sizes, 9) == 9
     assert list(sizes) == L.struct_sizes() == [theirs[c] for c in ("sdemc_sde", "sdemc_payoff", "sdemc_range",
                                                                     "sdemc_inject", "sdemc_moments",
-                                                                    "sdemc_paths_out", "sdemc_mlp")]
+                                                                    "sdemc_paths_out", "sdemc_mlp", "sdemc_coeffs_f64",
+                                                                    "sdemc_inject_f64")]
 
 
 def test_integration_md_binding_snippet_lays_out_the_same_structs():

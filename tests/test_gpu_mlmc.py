@@ -39,6 +39,62 @@ def test_jump_pair_vs_reference_golden(name):
     assert rel_err(_np(pc)[:, -1], g["coarse_last"]) < 5e-5
 
 
+@pytest.mark.parametrize("name", sorted(MLMC_CASES))
+def test_jump_pair_fp64_vs_reference_golden(name):
+    """sdemc_mlmc_pair_f64 (fp64 state, coefficients, marks) on the reference's fp64 noise: the terminal states of the
+    reference's own fp64 coupled pair (solvers.py:228-307 under set_default_dtype(float64)) to 1e-12"""
+    g = golden(name)
+    fine, coarse = mlmc_levels(name)
+    torch.set_default_dtype(torch.float64)       # the reference's switch for its jump MLMC; selects the fp64 kernel
+    try:
+        solver = sm.JumpEulerSolver(MLMC_CASES[name](g), float(g["T"]), fine, device=DEV,
+                                    exact_jumps=bool(int(g["exact_jumps"])))
+        inject = dict(z=g["z"], jump_times=g["jump_times"], marks=g["marks"])
+        if "zc" in g.files:
+            inject["zc"] = g["zc"]
+        (pf, pc), _ = solver.multilevel_solve(g["z"].shape[0], (fine, coarse), inject=inject)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert pf.dtype == torch.float64
+    assert rel_err(_np(pf)[:, -1], g["fine_last"]) < 1e-12
+    assert rel_err(_np(pc)[:, -1], g["coarse_last"]) < 1e-12
+
+
+def test_fp64_pair_large_inject_vs_fp64_oracle_and_philox_levels():
+    """(1) 4096 pairs of injected fp64 noise against the fp64 oracle at 1e-12; (2) Philox-driven fp64 pairs consume the
+    counters of the fp32 pair kernel: per-level moments of P_f - P_c agree to fp32 accuracy of the states, and the
+    fp64 run removes the fp32 rounding noise from the finest level's variance"""
+    rng = np.random.default_rng(15)
+    bs, fine, coarse = 4096, 32, 8
+    torch.set_default_dtype(torch.float64)
+    try:
+        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+        solver = sm.JumpEulerSolver(sde, 3, fine, device=DEV, exact_jumps=True)
+        K = coarse + solver.max_jumps
+        z = rng.standard_normal((bs, K * 4, 1))
+        jt = np.cumsum(rng.exponential(1.0, (bs, solver.max_jumps)), axis=1)
+        mk = rng.standard_normal((bs, K))
+        fl, cl, iters, total = oracle.jump_pair(oracle_sde(solver, fine), fine, coarse, z, None, jt, mk, np.float64)
+        (pf, pc), _ = solver.multilevel_solve(bs, (fine, coarse), inject=dict(z=z, jump_times=jt, marks=mk))
+        assert rel_err(_np(pf)[:, -1], fl) < 1e-12 and rel_err(_np(pc)[:, -1], cl) < 1e-12
+        from sde_mc_b200.mlmc import _level_moments
+        call, csr = sm.EuroCall(1.0), sm.ConstantShortRate(0.02)
+        n = 200_000
+        s64 = sm.JumpEulerSolver(sde, 3, 1, device=DEV, seed=3, exact_jumps=True)
+        m64 = _level_moments(s64, call, csr, n, 128, 64).read()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1)
+    s32 = sm.JumpEulerSolver(sde, 3, 1, device=DEV, seed=3, exact_jumps=True)
+    m32 = _level_moments(s32, call, csr, n, 128, 64).read()
+    assert m64["n"] == m32["n"] == n and m64["iters"] == m32["iters"]          # same draws, same clock
+    mean64, mean32 = m64["sum"] / n, m32["sum"] / n
+    assert abs(mean64 - mean32) < 2e-6                                          # same pairs up to fp32 rounding of the states
+    var64 = m64["sumsq"] / n - mean64 ** 2
+    var32 = m32["sumsq"] / n - mean32 ** 2
+    assert 0 < var64 <= var32 * 1.02                                            # fp32 adds rounding noise, never removes it
+
+
 def test_diffusion_pair_vs_reference_golden():
     g = golden("diff_gbm_mlmc_8_2")
     solver = sm.EulerSolver(sm.Gbm(0.02, 0.3, t(g["x0"]), 1), float(g["T"]), 8, device=DEV)

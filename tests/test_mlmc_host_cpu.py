@@ -9,12 +9,18 @@ from common import sm  # noqa: F401  (puts the repo on sys.path)
 from sde_mc_b200 import mlmc as M
 
 
-class _FakeMoments:
-    def __init__(self, total, total_sq, n):
-        self._d = {"sum": total, "sumsq": total_sq, "n": float(n), "iters": 0.0}
+class _FakeLevels:
+    """stands in for mlmc.LevelMoments: read() -> one moments dict per level"""
+
+    def __init__(self, rows):
+        self._rows = rows
 
     def read(self):
-        return self._d
+        return self._rows
+
+
+def _FakeMoments(total, total_sq, n):
+    return {"sum": total, "sumsq": total_sq, "n": float(n), "iters": 0.0}
 
 
 class _FakeSolver:
@@ -33,8 +39,8 @@ def test_get_optimal_trials_is_the_reference_allocation(monkeypatch):
     levels = [1, 2, 4, 8]
     variances = [2.97e-1, 7.8e-3, 6.0e-3, 3.8e-3]          # level variances of C5
     pilot = 10 ** 5
-    monkeypatch.setattr(M, "_all_levels", lambda solver, payoff, disc, trials, lv: [
-        _moments_with(0.1, v, n) for v, n in zip(variances, trials)])
+    monkeypatch.setattr(M, "_all_levels", lambda solver, payoff, disc, trials, lv: _FakeLevels([
+        _moments_with(0.1, v, n) for v, n in zip(variances, trials)]))
     solver = _FakeSolver()
     eps = 1e-3
     got = M.get_optimal_trials(pilot, levels, eps, solver, None, None)
@@ -51,8 +57,8 @@ def test_mc_multilevel_telescopes_means_and_adds_variances(monkeypatch):
     trials = [1000, 400, 100]
     means = [0.25, 0.01, 0.003]
     variances = [0.3, 0.008, 0.006]
-    monkeypatch.setattr(M, "_all_levels", lambda solver, payoff, disc, tr, lv: [
-        _moments_with(m, v, n) for m, v, n in zip(means, variances, tr)])
+    monkeypatch.setattr(M, "_all_levels", lambda solver, payoff, disc, tr, lv: _FakeLevels([
+        _moments_with(m, v, n) for m, v, n in zip(means, variances, tr)]))
     st = M.mc_multilevel(trials, levels, _FakeSolver(), None, None)
     assert abs(st.sample_mean - sum(means)) < 1e-12
     assert abs(st.sample_std - math.sqrt(sum(v / n for v, n in zip(variances, trials)))) < 1e-12
