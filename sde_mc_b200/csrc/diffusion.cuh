@@ -45,7 +45,7 @@ constexpr int kDiffusionStoreBlock = 128;  // threads per CTA of the storing ker
 // register limit (47 at 5 CTAs per SM): keeping the path index alive across the step loop for three predicated
 // stores cost 4.6 % of the C2 throughput (measured, 1.586e12 vs 1.662e12).  Both instantiations are the same source;
 // tests/test_gpu_fastpath.py ties them: the fp64 sums of the plain launch equal those of the PERPATH launch bit for bit.
-template <class C, bool HESTON, bool INJECT, bool STORE, bool PERPATH = false>
+template <class C, bool HESTON, bool INJECT, bool STORE, bool PERPATH = false, int RMODE = RANGE_HOST>
 __global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, STORE>()) diffusion_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                         const PhiloxKeys keys, const DevInject inj, const DevOut out,
                                                         double* __restrict__ d_moments, void* __restrict__ d_ws) {
@@ -66,19 +66,19 @@ __global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, S
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   // warp-uniform trip count: in STORE mode all 32 lanes stage their outputs in lock-step, so lanes past the end of
   // the range keep iterating (their rows are never written)
-  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < range_n(rg); wbase += stride) {
+  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < range_n<RMODE>(rg); wbase += stride) {
     const uint64_t i = wbase + (threadIdx.x & 31);
-    if (!STORE && i >= range_n(rg)) break;
-    const bool valid = i < range_n(rg);
-    const uint64_t gp = range_lo(rg) + i;
+    if (!STORE && i >= range_n<RMODE>(rg)) break;
+    const bool valid = i < range_n<RMODE>(rg);
+    const uint64_t gp = range_lo<RMODE>(rg) + i;
     const uint32_t plo = (uint32_t)gp, phi = (uint32_t)(gp >> 32);
     float x[kMaxDim];
 #pragma unroll
     for (int d = 0; d < kMaxDim; ++d) x[d] = d < DIM ? s.x0[d] : 0.0f;
     if (STORE) {
       float* tiles = diff_store_smem + (threadIdx.x >> 5) * (2 * Writer::kFloats);
-      wpaths.init(tiles, out.paths, out.pitch_state, wbase, range_n(rg));
-      wnorm.init(tiles + Writer::kFloats, out.normals, out.pitch_normals, wbase, range_n(rg));
+      wpaths.init(tiles, out.paths, out.pitch_state, wbase, range_n<RMODE>(rg));
+      wnorm.init(tiles + Writer::kFloats, out.normals, out.pitch_normals, wbase, range_n<RMODE>(rg));
 #pragma unroll
       for (int d = 0; d < DIM; ++d) wpaths.append(x[d]);
     }

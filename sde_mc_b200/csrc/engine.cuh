@@ -60,6 +60,15 @@ __device__ __forceinline__ uint64_t range_dyn_word(const DevRange& rg, int w) {
 }
 __device__ __forceinline__ uint64_t range_n(const DevRange& rg) { return rg.dyn ? range_dyn_word(rg, 1) : rg.n_paths; }
 __device__ __forceinline__ uint64_t range_lo(const DevRange& rg) { return rg.dyn ? range_dyn_word(rg, 0) : rg.path_lo; }
+// The same with the choice made at compile time, for the kernels in which a few instructions per path or two live
+// registers are measurable: the 1-D uniform-grid kernel sits at its register limit (the run-time form cost 3 % of the
+// C2 throughput: 1.608e12 vs 1.659e12) and the short-path kernels spend ~340 instructions on a whole path (3 % of an
+// MLMC pass).  RANGE_HOST: the constant-bank reads these kernels always had; RANGE_DEVICE: device memory.
+enum { RANGE_HOST = 0, RANGE_DEVICE = 1 };
+template <int MODE>
+__device__ __forceinline__ uint64_t range_n(const DevRange& rg) { return MODE == RANGE_DEVICE ? range_dyn_word(rg, 1) : rg.n_paths; }
+template <int MODE>
+__device__ __forceinline__ uint64_t range_lo(const DevRange& rg) { return MODE == RANGE_DEVICE ? range_dyn_word(rg, 0) : rg.path_lo; }
 
 struct DevInject {
   const float* z;

@@ -16,7 +16,7 @@
 namespace sdemc {
 
 // 3 CTAs per SM: 80 registers keep the per-path setup free of spills (measured +5 % on the C5 pass against 4)
-template <class C>
+template <class C, bool PERPATH = false, int RMODE = RANGE_HOST>
 __global__ void __launch_bounds__(256, 3)
     jump_flat_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys,
                      const DevPerPath pp, double* __restrict__ d_moments, void* __restrict__ d_ws) {
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256, 3)
   const int kcap = 4 * (n + s.max_jumps) + 64;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = i < range_n(rg);
+  bool live = i < range_n<RMODE>(rg);
 
   JumpState st;
   Src src;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256, 3)
   int b = 0;          // group index inside the current path
   float xs[kMaxDim];  // state at array index num_steps ('terminal' payoff index)
   auto start_path = [&](uint64_t idx) {
-    const uint64_t gp = range_lo(rg) + idx;
+    const uint64_t gp = range_lo<RMODE>(rg) + idx;
     plo = (uint32_t)gp;
     phi = (uint32_t)(gp >> 32);
 #pragma unroll
@@ -81,9 +81,9 @@ __global__ void __launch_bounds__(256, 3)
       for (int d = 0; d < kMaxDim; ++d) xp[d] = (po.index_mode == SDEMC_INDEX_TERMINAL && st.k >= n) ? xs[d] : st.x[d];
       const float pay = eval_payoff<DIM>(po, xp);
       acc.add(pay, po.df * st.x[0] - s.x0[0], st.k);
-      write_per_path<DIM>(pp, i, pay, st.k, xp);
+      if (PERPATH) write_per_path<DIM>(pp, i, pay, st.k, xp);
       i += stride;
-      live = i < range_n(rg);
+      live = i < range_n<RMODE>(rg);
       if (live) start_path(i);
     }
   }
@@ -145,7 +145,7 @@ __device__ __forceinline__ void packed_block_draws(uint32_t b, uint32_t plo, uin
 // radius (one square root per iteration), the jump coefficient folded into the mark -- about 16
 // instructions instead of the ~45 of the generic jump_iteration (geometric Euler only; Milstein takes the generic
 // form).  Same draws, same mesh and hits; the state agrees to fp32 rounding (test: sums to 1e-5, iterations equal).
-template <class C, bool FAST>
+template <class C, bool FAST, bool PERPATH = false, int RMODE = RANGE_HOST>
 __global__ void __launch_bounds__(256, 3)
     jump_flat1d_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys,
                        const DevPerPath pp, double* __restrict__ d_moments, void* __restrict__ d_ws) {
@@ -158,14 +158,14 @@ __global__ void __launch_bounds__(256, 3)
   const int kcap = 4 * (n + s.max_jumps) + 64;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = i < range_n(rg);
+  bool live = i < range_n<RMODE>(rg);
 
   JumpState st;
   Src src;
   uint32_t plo = 0, phi = 0;
   float x_at_n = 0.0f;  // state at array index num_steps ('terminal' payoff index)
   auto start_path = [&](uint64_t idx) {
-    const uint64_t gp = range_lo(rg) + idx;
+    const uint64_t gp = range_lo<RMODE>(rg) + idx;
     plo = (uint32_t)gp;
     phi = (uint32_t)(gp >> 32);
 #pragma unroll
@@ -222,9 +222,9 @@ __global__ void __launch_bounds__(256, 3)
       xp[0] = (po.index_mode == SDEMC_INDEX_TERMINAL && st.k >= n) ? x_at_n : st.x[0];
       const float pay = eval_payoff<1>(po, xp);
       acc.add(pay, po.df * st.x[0] - s.x0[0], st.k);
-      write_per_path<1>(pp, i, pay, st.k, xp);
+      if (PERPATH) write_per_path<1>(pp, i, pay, st.k, xp);
       i += stride;
-      live = i < range_n(rg);
+      live = i < range_n<RMODE>(rg);
       if (live) start_path(i);
     }
   }

@@ -61,9 +61,9 @@ int run_store_tma(const LaunchArgs& a) {
   return SDEMC_OK;
 }
 
-template <class C, bool HESTON, bool INJECT, bool STORE, bool PERPATH = false>
+template <class C, bool HESTON, bool INJECT, bool STORE, bool PERPATH = false, int RMODE = RANGE_HOST>
 int run(const LaunchArgs& a) {
-  auto kernel = diffusion_kernel<C, HESTON, INJECT, STORE, PERPATH>;
+  auto kernel = diffusion_kernel<C, HESTON, INJECT, STORE, PERPATH, RMODE>;
   const int block = STORE ? kDiffusionStoreBlock : kBlock;
   const size_t smem = STORE ? (size_t)(block / 32) * 2 * DiffusionStoreWriter<C>::kFloats * sizeof(float) : 0;
   if (smem > 48 * 1024)
@@ -86,6 +86,7 @@ int by_mode(const LaunchArgs& a) {
   }
   if (a.use_inject) return SDEMC_ERR_UNSUPPORTED;  // injected noise is only offered with stored outputs
   if (per_path_of_out(a.out).any()) return run<C, HESTON, false, false, true>(a);
+  if (a.range.dyn) return run<C, HESTON, false, false, false, RANGE_DEVICE>(a);   // range read from device memory
   return run<C, HESTON, false, false>(a);
 }
 

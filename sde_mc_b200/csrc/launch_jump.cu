@@ -57,10 +57,10 @@ int run_1d(const LaunchArgs& a) {
   return sat ? run_1d_inst<C, EXACT, false, true>(a) : run_1d_inst<C, EXACT, false, false>(a);
 }
 
-// moments-only kernel for short paths with inline jumps: lanes are persistent workers (jump_flat.cuh)
-template <class C>
-int run_flat(const LaunchArgs& a) {
-  auto kernel = jump_flat_kernel<C>;
+// moments-only kernel for short paths with inline jumps: lanes are persistent workers (jump_flat.cuh).  The per-path
+// hook and the device-resident range are compile-time variants here: a whole path is ~340 instructions.
+template <class Kernel>
+int launch_flat(Kernel kernel, const LaunchArgs& a) {
   int grid = 0;
   int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
   if (rc != SDEMC_OK) return rc;
@@ -68,17 +68,19 @@ int run_flat(const LaunchArgs& a) {
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
 }
+template <class C>
+int run_flat(const LaunchArgs& a) {
+  if (per_path_of_out(a.out).any()) return launch_flat(jump_flat_kernel<C, true, RANGE_HOST>, a);
+  if (a.range.dyn) return launch_flat(jump_flat_kernel<C, false, RANGE_DEVICE>, a);
+  return launch_flat(jump_flat_kernel<C, false, RANGE_HOST>, a);
+}
 
 // 1-D lognormal-mark models: two iterations per Philox block, no alignment across the warp (jump_flat.cuh)
 template <class C, bool FAST>
 int run_flat1d(const LaunchArgs& a) {
-  auto kernel = jump_flat1d_kernel<C, FAST>;
-  int grid = 0;
-  int rc = pick_grid(kernel, 0, a.range.n_paths, &grid);
-  if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kBlock, 0, a.stream>>>(a.sde, a.payoff, a.range, a.keys, per_path_of_out(a.out), a.d_moments, a.d_ws);
-  SDEMC_CUDA_CHECK(cudaGetLastError());
-  return SDEMC_OK;
+  if (per_path_of_out(a.out).any()) return launch_flat(jump_flat1d_kernel<C, FAST, true, RANGE_HOST>, a);
+  if (a.range.dyn) return launch_flat(jump_flat1d_kernel<C, FAST, false, RANGE_DEVICE>, a);
+  return launch_flat(jump_flat1d_kernel<C, FAST, false, RANGE_HOST>, a);
 }
 
 // A warp of jump_kernel runs until its slowest lane is done: E[max of 32 Poisson(rate T)] exceeds the mean by about
