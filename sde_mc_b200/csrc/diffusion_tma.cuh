@@ -71,13 +71,19 @@ struct TmaRowWriter {
   // `issued`: bulk groups this thread has committed so far, shared by all writers of the warp.  The tile we switch
   // to was last copied out as group seq_other; only groups newer than that may still be reading shared memory.
   __device__ __forceinline__ void flush(int& issued) {
+#ifndef SDEMC_TMA_NO_FENCE   // (timing experiments only: the copy may then read stale shared memory)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my staging stores -> visible to the TMA engine
+#endif
     __syncwarp();
     const int my_seq = ++issued;
     if ((threadIdx.x & 31) == 0) {
       tma_store_tile(map, cur, col, row0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       const int allowed = my_seq - seq_other;  // wait_group takes an immediate; fewer pending than allowed is safe
+#ifdef SDEMC_TMA_NO_WAIT      // (timing experiments only: tiles may be overwritten while still being copied)
+      if (false) {}
+      else
+#endif
       if (allowed >= 4) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
       else if (allowed == 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
       else if (allowed == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
