@@ -213,8 +213,9 @@ typedef struct {
 } sdemc_paths_out;
 
 /* Control-variate networks for the fused CV kernel: the BN-free Mlp of nets.py:39-93,
- * Linear(d+1,H) ReLU Linear(H,H) ReLU Linear(H,H) ReLU Linear(H,out). Weights are torch Linear
- * layouts (out_features, in_features) row-major fp32, device pointers. */
+ * Linear(d+1,H) ReLU Linear(H,H) ReLU Linear(H,H) ReLU Linear(H,out), H <= 63. Weights are torch Linear
+ * layouts (out_features, in_features) row-major fp32, device pointers.  out = dim * m for f (one output per Brownian
+ * driver of every component, integrate_cv varred.py:202-214) and dim for g (varred.py:124). */
 typedef struct {
   uint32_t struct_size; /* sizeof(sdemc_mlp) */
   uint32_t reserved;
@@ -295,7 +296,9 @@ int sdemc_mlmc_pair_f64(const sdemc_sde* sde, const sdemc_coeffs_f64* coeffs, co
 
 /* E5/E6/E7 fused: simulate + evaluate the control-variate MLPs f, g along each path on tensor cores and
  * accumulate gamma = payoff + sum f dW D + sum g D J - sum rate E[J] g D h  (varred.py:98-131).
- * g may be NULL for pure diffusions (varred.py:75-95). jump_mean = sde.jump_mean(). */
+ * g may be NULL for pure diffusions (varred.py:75-95). jump_mean = sde.jump_mean().
+ * Model shapes: 1-D geometric 'diag' SDEs (Gbm, Merton: merton_cv_experiment.py) and the 2-D geometric 'indep'
+ * inverse-cdf-mark SDE (LevySde(ExpExampleLevy, dim=2): levy_rainbow_cv_experiment.py:39-40); others UNSUPPORTED. */
 int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rate, float jump_mean,
                 const sdemc_mlp* f, const sdemc_mlp* g, const sdemc_range* range, const sdemc_inject* inject,
                 sdemc_moments* d_moments, float* d_gamma_out /* (n) or NULL */, void* d_workspace, void* stream);

@@ -262,11 +262,12 @@ int sdemc_mlmc_pair_f64(const sdemc_sde* sde, const sdemc_coeffs_f64* co, const 
                          reinterpret_cast<double*>(d_moments), d_pair_out, d_workspace, reinterpret_cast<cudaStream_t>(stream));
 }
 
-static bool mlp_ok(const sdemc_mlp* m) {
+// f has dim * m outputs (one per driver of every component), g has dim; both see (t, x): dim + 1 inputs
+static bool mlp_ok(const sdemc_mlp* m, int in_dim, int out_dim) {
   if (!sized(m)) return false;
   for (int i = 0; i < 4; ++i)
     if (!m->d_w[i] || !m->d_b[i]) return false;
-  return m->in_dim == 2 && m->out_dim == 1 && m->n_hidden_layers == 3 && m->hidden >= 1 && m->hidden <= 63;
+  return m->in_dim == in_dim && m->out_dim == out_dim && m->n_hidden_layers == 3 && m->hidden >= 1 && m->hidden <= 63;
 }
 static DevMlp mlp_dev(const sdemc_mlp* m) {
   DevMlp d;
@@ -284,11 +285,12 @@ int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rat
   if (!valid_sde(sde) || !sized(payoff) || !sized(range) || !d_moments || !d_workspace) return SDEMC_ERR_BAD_ARG;
   if (!sized_or_null(inject) || !sized_or_null(f) || !sized_or_null(g)) return SDEMC_ERR_BAD_ARG;
   const bool jumps = sde->marks != SDEMC_MARKS_NONE;
-  if (!mlp_ok(f) || (jumps && !mlp_ok(g))) return SDEMC_ERR_UNSUPPORTED;
+  if (!mlp_ok(f, sde->dim + 1, sde->dim * sde->m) || (jumps && !mlp_ok(g, sde->dim + 1, sde->dim))) return SDEMC_ERR_UNSUPPORTED;
   if (range->n_paths == 0 && !range->d_range) return SDEMC_OK;
   if (inject) {
     if (!inject->d_z || inject->K < 1) return SDEMC_ERR_BAD_ARG;
     if (jumps && (!inject->d_jump_times || !inject->d_marks)) return SDEMC_ERR_BAD_ARG;
+    if (jumps && sde->m == 2 && !inject->d_zc) return SDEMC_ERR_BAD_ARG;
     if (!jumps && inject->K != sde->num_steps) return SDEMC_ERR_BAD_ARG;
   }
   LaunchArgs a;

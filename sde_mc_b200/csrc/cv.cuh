@@ -149,6 +149,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// N consecutive columns (N = 1, 2 or 4) of this warp's lanes: the head outputs of a net
+template <int N>
+__device__ __forceinline__ void tmem_ld_small(uint32_t taddr, uint32_t (&v)[4]) {
+  static_assert(N == 1 || N == 2 || N == 4, "head widths");
+  if constexpr (N == 1) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr));
+  else if constexpr (N == 2) asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+  else asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -186,16 +194,24 @@ struct CvAccRow {
     tmem_st16(ta + 16, a);
   }
 };
-// first-layer activation vector (K = 16 -> 8 columns): [t_hi, t_lo | x_hi, x_lo | 1, 0 | 0 ...]
-__device__ __forceinline__ void write_input_row(uint32_t ta, float t, float x) {
-  const __nv_bfloat16 th = __float2bfloat16_rn(t), xh = __float2bfloat16_rn(x);
-  const __nv_bfloat16 tl = __float2bfloat16_rn(t - __bfloat162float(th)), xl = __float2bfloat16_rn(x - __bfloat162float(xh));
+// bf16 (hi, lo) split of an fp32 input: hi + lo carries 16 mantissa bits, both K slots use the same weight
+__device__ __forceinline__ uint32_t split_bf16(float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+}
+// first-layer activation vector (K = 16 -> 8 columns): [t_hi, t_lo | x0_hi, x0_lo | ... | 1, 0 | 0 ...]; NX = state
+// dimension (inputs (t, x_0 .. x_{NX-1}), nets.py:39-93 with input_dim = dim + 1), at most 6
+template <int NX>
+__device__ __forceinline__ void write_input_row(uint32_t ta, float t, const float (&x)[kMaxDim]) {
+  static_assert(NX >= 1 && NX <= 6, "first-layer K = 16 holds (t, x) as hi/lo pairs plus the bias slot");
   uint32_t a[8];
-  a[0] = (uint32_t)__bfloat16_as_ushort(th) | ((uint32_t)__bfloat16_as_ushort(tl) << 16);
-  a[1] = (uint32_t)__bfloat16_as_ushort(xh) | ((uint32_t)__bfloat16_as_ushort(xl) << 16);
-  a[2] = 0x00003f80u;  // (1.0bf16, 0)
+  a[0] = split_bf16(t);
 #pragma unroll
-  for (int c = 3; c < 8; ++c) a[c] = 0u;
+  for (int j = 0; j < NX; ++j) a[1 + j] = split_bf16(x[j]);
+  a[1 + NX] = 0x00003f80u;  // (1.0bf16, 0): the bias slot
+#pragma unroll
+  for (int c = 2 + NX; c < 8; ++c) a[c] = 0u;
   tmem_st8(ta, a);
 }
 
@@ -205,11 +221,11 @@ __device__ __forceinline__ void load_mlp(const DevMlp& net, uint8_t* w1, uint8_t
   for (int idx = threadIdx.x; idx < 64 * 16; idx += blockDim.x) {
     const int n = idx >> 4, k = idx & 15;
     float v = 0.0f;
+    const int nin = net.in_dim;  // inputs (t, x_0, ...): slots 2j, 2j+1 = hi, lo of input j; slot 2 nin = bias
     if (n < H) {
-      if (k < 2) v = net.w[0][n * 2 + 0];
-      else if (k < 4) v = net.w[0][n * 2 + 1];
-      else if (k == 4) v = net.b[0][n];
-    } else if (n == kCvOne && k == 4) {
+      if (k < 2 * nin) v = net.w[0][n * nin + (k >> 1)];
+      else if (k == 2 * nin) v = net.b[0][n];
+    } else if (n == kCvOne && k == 2 * nin) {
       v = 1.0f;
     }
     *reinterpret_cast<__nv_bfloat16*>(w1 + (k >> 3) * (64 * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(v);
@@ -228,11 +244,11 @@ __device__ __forceinline__ void load_mlp(const DevMlp& net, uint8_t* w1, uint8_t
       *reinterpret_cast<__nv_bfloat16*>(dst + (k >> 3) * (64 * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(v);
     }
   }
-  // head: B operand of kCvHeadN rows, row 0 = (w4, bias in the constant-one slot), the other rows zero
+  // head: B operand of kCvHeadN rows, rows 0 .. out_dim-1 = (w4 row, bias in the constant-one slot), the rest zero
   for (int idx = threadIdx.x; idx < kCvHeadN * 64; idx += blockDim.x) {
     const int n = idx >> 6, k = idx & 63;
     float v = 0.0f;
-    if (n == 0) v = k < H ? net.w[3][k] : (k == kCvOne ? net.b[3][0] : 0.0f);
+    if (n < net.out_dim) v = k < H ? net.w[3][n * H + k] : (k == kCvOne ? net.b[3][n] : 0.0f);
     *reinterpret_cast<__nv_bfloat16*>(w4 + (k >> 3) * (kCvHeadN * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(v);
   }
 }
@@ -252,7 +268,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// 1-D 'diag' SDE (dim == 1, m == 1): Merton-type jump diffusion (JUMPS) or GBM-type diffusion (!JUMPS)
+// Model shapes (launch_cv.cu): 1-D 'diag' SDEs (dim == 1, m == 1: Merton-type jump diffusion or GBM-type
+// diffusion, nets Mlp(2, [H, H, H], 1): merton_cv_experiment.py:37-38) and the 2-D 'indep' exp-Levy SDE of
+// levy_rainbow_cv_experiment.py:39-40 (dim == 2, m == 2: f = Mlp(3, [H, H, H], 4), g = Mlp(3, [H, H, H], 2)).  In
+// general f has dim * m outputs -- f_{d,j} multiplies the increment of driver j of component d, integrate_cv
+// varred.py:202-214 -- and g has dim outputs, all multiplying the ONE common jump mark of the path (varred.py:124).
 //
 // Warp roles: warps 4*tl .. 4*tl+3 are the workers of tile tl (thread = path = TMEM lane; a warp can only access the
 // TMEM lanes of its quadrant, warp % 4); warp kCvWorkerWarps + tl is the MMA issuer of tile tl (one thread).
@@ -375,8 +395,16 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
     }
   } else {
     // ======================================== workers ==========================================================
+    constexpr int DIM = C::DIM, M = C::M, BASE = C::BASE;
+    constexpr int NF = DIM * M;                      // outputs of f: one per (component, driver)
+    constexpr int NG = DIM;                          // outputs of g: one per component
+    constexpr int NZ = BASE + (M == 2 ? 1 : 0);      // unit normals per iteration (jump solver: ONE common 2nd driver)
+    constexpr int LF = NF <= 1 ? 1 : (NF <= 2 ? 2 : 4), LG = NG <= 1 ? 1 : (NG <= 2 ? 2 : 4);
+    static_assert(NF <= 4 && NZ <= 4 && !C::ASIAN, "head widths / one Philox block of normals per iteration");
+    constexpr bool SHARE4 = NZ == 1;                 // 1-D: one Philox block serves four iterations
     struct Path {
-      float x, t, left, Jprev, cvsum;
+      float x[kMaxDim], left[kMaxDim];
+      float t, Jprev, cvsum;
       float zbuf[4];
       uint64_t i;
       uint32_t plo, phi;
@@ -437,31 +465,41 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
       if (!early) release();
     };
     // One iteration of the path (solvers.py:182-225) and the weights its control-variate terms carry:
-    //   cvsum += cf * f(t_k, x_k) + cg * g(t_k, left_k)   with  cf = D dW,  cg = D (J_prev - rate E[J] dt)
-    // (integrate_cv varred.py:202-214, :124, :126-127).  Nothing here depends on the nets, so it runs while the
-    // tensor core works on the first phases of the step.
-    float cf = 0.0f, cg = 0.0f;
+    //   cvsum += sum_{d,j} cf[d,j] f_{d,j}(t_k, x_k) + cg sum_d g_d(t_k, left_k)
+    // with cf[d,j] = D dW_{d,j} and cg = D (J_prev - rate E[J] dt)   (integrate_cv varred.py:202-214, :124, :126-127;
+    // the jump mark is common to all components, solvers.py:146-148).  Nothing here depends on the nets, so it runs
+    // while the tensor core works on the first phases of the step.
+    float cf[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cg = 0.0f;
     bool cv_live = false;  // the path was active in the iteration just advanced (finished paths add nothing)
     auto advance_path = [&](int k) {
       const bool active = is_active(p, k);
       const float t_in = t_input(p, k);
-      // this thread's Brownian normal for iteration k (one Philox block serves 4 iterations)
-      if ((k & 3) == 0) {
-        if constexpr (!INJECT) {
+      // this thread's unit normals for iteration k: one Philox block = four normals (two full Box-Muller pairs) serves
+      // four iterations of a single-driver path, or one iteration of up to four drivers
+      float zn[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if constexpr (INJECT) {
+        if (p.valid && k < inj.K) {
+#pragma unroll
+          for (int d = 0; d < BASE; ++d) zn[d] = inj.z[(p.i * (uint64_t)inj.K + k) * DIM + d];
+          if (M == 2) zn[BASE] = inj.zc[p.i * (uint64_t)inj.K + k];
+        }
+      } else if constexpr (SHARE4) {
+        if ((k & 3) == 0) {
           uint32_t o[4];
           philox4x32_10((uint32_t)(k >> 2), STREAM_DIFFUSION, p.plo, p.phi, keys, o);
           box_muller(o[0], o[1], p.zbuf[0], p.zbuf[1]);
           box_muller(o[2], o[3], p.zbuf[2], p.zbuf[3]);
         }
-      }
-      float z;
-      if constexpr (INJECT) {
-        z = (p.valid && k < inj.K) ? inj.z[p.i * (uint64_t)inj.K + k] : 0.0f;
-      } else {
-        z = p.zbuf[0];
+        zn[0] = p.zbuf[0];
         p.zbuf[0] = p.zbuf[1]; p.zbuf[1] = p.zbuf[2]; p.zbuf[2] = p.zbuf[3];
+      } else {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)k, STREAM_DIFFUSION, p.plo, p.phi, keys, o);
+        box_muller(o[0], o[1], zn[0], zn[1]);
+        box_muller(o[2], o[3], zn[2], zn[3]);
       }
-      cf = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cf[q] = 0.0f;
       cg = 0.0f;
       cv_live = active;
       if (active) {
@@ -478,22 +516,37 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
           dt = s.h0;
           sq = s.sqrt_h0;
         }
-        float xv[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f}, xo[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
-        float w1[kMaxDim] = {z, 0.0f, 0.0f, 0.0f}, w2[kMaxDim] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float xv[kMaxDim], xo[kMaxDim], z1[kMaxDim], w1[kMaxDim], w2[kMaxDim];
+#pragma unroll
+        for (int d = 0; d < kMaxDim; ++d) {
+          xv[d] = xo[d] = p.x[d];
+          z1[d] = d < BASE ? zn[d] : 0.0f;
+          w2[d] = (M == 2 && d < BASE) ? zn[BASE] : 0.0f;   // the second driver is one scalar normal (:198-201)
+        }
+        correlate<C>(s, z1, w1);
         euler_step<C>(s, xv, dt, sq, w1, w2);
-        cf = D * (z * sq);                                         // f dW
+#pragma unroll
+        for (int d = 0; d < BASE; ++d) {
+          cf[d * M] = D * (w1[d] * sq);                              // f_{d,0} dW_{d,0}
+          if (M == 2) cf[d * M + 1] = D * (zn[BASE] * sq);           // f_{d,1} dW_{.,1}: the common driver
+        }
         if constexpr (JUMPS) {
           cg = D * (k < cv.last_interval ? fmaf(cv.comp_c, dt, p.Jprev) : p.Jprev);  // g J - rate E[J] g dt
           p.t += dt;
-          p.left = xv[0];
+#pragma unroll
+          for (int d = 0; d < kMaxDim; ++d) p.left[d] = xv[d];
           const bool hit = fabsf(tau - p.t) <= fmaf(fabsf(p.t), 1e-5f, 1e-12f);
           const float Jc = hit ? p.src.mark(s, k) : 0.0f;
-          if (s.exact_jumps) xo[0] = xv[0];
+          if (s.exact_jumps) {
+#pragma unroll
+            for (int d = 0; d < kMaxDim; ++d) xo[d] = xv[d];
+          }
           add_jump<C>(s, xv, xo, Jc);
           p.Jprev = Jc;
           p.need_pop = hit;
         }
-        p.x = xv[0];
+#pragma unroll
+        for (int d = 0; d < kMaxDim; ++d) p.x[d] = xv[d];
         p.own_iters = k + 1;
       }
     };
@@ -507,9 +560,9 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
         p.plo = (uint32_t)gp;
         p.phi = (uint32_t)(gp >> 32);
       }
-      p.x = s.x0[0];
+#pragma unroll
+      for (int d = 0; d < kMaxDim; ++d) p.x[d] = p.left[d] = d < DIM ? s.x0[d] : 0.0f;
       p.t = 0.0f;
-      p.left = s.x0[0];
       p.Jprev = 0.0f;
       p.cvsum = 0.0f;
       p.own_iters = 0;
@@ -520,8 +573,8 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
         if constexpr (INJECT) p.src.init(s, inj, p.valid ? p.i : 0);
         else p.src.init(p.plo, p.phi);
       }
-      write_input_row(t_af, t_input(p, 0), p.x);
-      if (JUMPS) write_input_row(t_ag, t_input(p, 0), p.left);
+      write_input_row<DIM>(t_af, t_input(p, 0), p.x);
+      if (JUMPS) write_input_row<DIM>(t_ag, t_input(p, 0), p.left);
       tmem_wait_st();
       if (is_active(p, 0)) flags[mine * 2 + 0] = 1;
       release();
@@ -542,18 +595,22 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
         }
         // ---- heads: both nets evaluated at the state of index k ---------------------------------------------------
         {
-          uint32_t hf, hg = 0u;
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(hf) : "r"(t_d));
-          if (JUMPS) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(hg) : "r"(t_d + kCvHeadN));
+          uint32_t hf[4] = {0u, 0u, 0u, 0u}, hg[4] = {0u, 0u, 0u, 0u};
+          tmem_ld_small<LF>(t_d, hf);
+          if (JUMPS) tmem_ld_small<LG>(t_d + kCvHeadN, hg);
           tmem_wait_ld();
           if (cv_live) {
-            p.cvsum = fmaf(cf, __uint_as_float(hf), p.cvsum);
-            if (JUMPS) p.cvsum = fmaf(cg, __uint_as_float(hg), p.cvsum);
+#pragma unroll
+            for (int q = 0; q < NF; ++q) p.cvsum = fmaf(cf[q], __uint_as_float(hf[q]), p.cvsum);
+            if (JUMPS) {
+#pragma unroll
+              for (int q = 0; q < NG; ++q) p.cvsum = fmaf(cg, __uint_as_float(hg[q]), p.cvsum);
+            }
           }
         }
         // first-layer activation vectors of state k+1; the issuer starts the next step if any path of the tile goes on
-        write_input_row(t_af, t_input(p, k + 1), p.x);
-        if (JUMPS) write_input_row(t_ag, t_input(p, k + 1), p.left);
+        write_input_row<DIM>(t_af, t_input(p, k + 1), p.x);
+        if (JUMPS) write_input_row<DIM>(t_ag, t_input(p, k + 1), p.left);
         tmem_wait_st();
         if (is_active(p, k + 1)) flags[mine * 2 + ((k + 1) & 1)] = 1;
         release();
@@ -564,8 +621,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
       }
 
       if (p.valid) {
-        float xp[kMaxDim] = {p.x, 0.0f, 0.0f, 0.0f};
-        const float pay = eval_payoff<1>(po, xp);
+        const float pay = eval_payoff<DIM>(po, p.x);
         const float gamma = pay + p.cvsum;
         if (cv.gamma_out) cv.gamma_out[p.i] = gamma;
         acc.add(gamma, pay, p.own_iters);

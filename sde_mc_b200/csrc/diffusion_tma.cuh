@@ -76,7 +76,11 @@ struct TmaRowWriter {
 #endif
     __syncwarp();
     const int my_seq = ++issued;
+#ifdef SDEMC_TMA_NO_COPY     // (timing experiments only: nothing is written)
+    if (false) {
+#else
     if ((threadIdx.x & 31) == 0) {
+#endif
       tma_store_tile(map, cur, col, row0);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       const int allowed = my_seq - seq_other;  // wait_group takes an immediate; fewer pending than allowed is safe
@@ -98,6 +102,9 @@ struct TmaRowWriter {
   // four consecutive elements of this lane's path
   __device__ __forceinline__ void put4(float a, float b, float c, float d, int& issued) {
     const uint32_t addr = cur + lane_row + ((((uint32_t)vec) ^ swz) << 4);
+#ifdef SDEMC_TMA_NO_STS      // (timing experiments only)
+    if (a == 123.456f && b == c && d == 7.0f)
+#endif
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
     if (++vec == kTmaTileElems / 4) flush(issued);
   }

@@ -32,7 +32,13 @@ int run(Kernel kernel, const LaunchArgs& a, const DevMlp& f, const DevMlp& g, co
 }  // namespace
 
 int launch_cv(const sdemc_sde& s, const LaunchArgs& a, const DevMlp& f, const DevMlp& g, const DevCv& cv) {
-  if (s.dim != 1 || s.m != 1 || s.asian || s.family != SDEMC_FAMILY_GEOMETRIC) return SDEMC_ERR_UNSUPPORTED;
+  if (s.asian || s.family != SDEMC_FAMILY_GEOMETRIC || s.scheme != SDEMC_SCHEME_EULER) return SDEMC_ERR_UNSUPPORTED;
+  // the 2-D 'indep' exp-Levy SDE of levy_rainbow_cv_experiment.py:39-40: f = Mlp(3, .., 4), g = Mlp(3, .., 2)
+  if (s.dim == 2 && s.m == 2 && s.marks == SDEMC_MARKS_ICDF) {
+    using C = Cfg<SDEMC_FAMILY_GEOMETRIC, 2, 2, SDEMC_MARKS_ICDF, false>;
+    return a.use_inject ? run(cv_kernel<C, true, true>, a, f, g, cv) : run(cv_kernel<C, true, false>, a, f, g, cv);
+  }
+  if (s.dim != 1 || s.m != 1) return SDEMC_ERR_UNSUPPORTED;
   if (s.marks == SDEMC_MARKS_LOGNORMAL) {
     using C = Cfg<SDEMC_FAMILY_GEOMETRIC, 1, 1, SDEMC_MARKS_LOGNORMAL, false>;
     return a.use_inject ? run(cv_kernel<C, true, true>, a, f, g, cv) : run(cv_kernel<C, true, false>, a, f, g, cv);

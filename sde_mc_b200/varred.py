@@ -158,7 +158,7 @@ def apply_adapted_control_variates(models, dl, solver, discounter, tol=0):
 FUSED_CV_ENABLED = True   # set to False to force the stored-trajectory + PyTorch path for every net
 
 
-def _export_mlp(net, dev, keep):
+def _export_mlp(net, dev, keep, in_dim=2, out_dim=1):
     layers = net.mlp_layers() if hasattr(net, 'mlp_layers') else None
     if layers is None or len(layers) != 4:
         return None
@@ -175,16 +175,19 @@ def _export_mlp(net, dev, keep):
     m.n_hidden_layers = 3
     if layers[1][0].shape != (m.hidden, m.hidden) or layers[2][0].shape != (m.hidden, m.hidden) or m.hidden > 63:
         return None
-    if m.in_dim != 2 or m.out_dim != 1:
+    if m.in_dim != in_dim or m.out_dim != out_dim:
         return None
     return m
 
 
 def fused_cv_supported(models, solver, tol=0):
     """True when `sdemc_mc_cv` can evaluate these nets: BN-free Linear/ReLU stacks with three equal hidden layers of
-    width <= 63 (the architecture of the experiments, merton_cv_experiment.py:37-38), 1-D geometric 'diag' SDE
-    (Gbm, Merton), constant short rate, tol == 0."""
-    if tol != 0 or solver.sde.dim != 1 or solver.sde.diffusion_struct != 'diag':
+    width <= 63 (the architecture of the experiments) on a model shape the kernel is built for -- 1-D geometric
+    'diag' SDEs (Gbm, Merton: merton_cv_experiment.py:37-38, Mlp(2, .., 1)) and the 2-D geometric 'indep' Levy SDE
+    (levy_rainbow_cv_experiment.py:39-40, f = Mlp(3, .., 4), g = Mlp(3, .., 2)) -- with a constant short rate and
+    tol == 0 (the trimming of varred.py:203-209 cuts at an index of the BATCH's longest path; a fused kernel has no
+    batch, so tol > 0 keeps the stored-trajectory route)."""
+    if tol != 0:
         return False
     try:
         spec = _spec.spec_of(solver.sde)
@@ -192,13 +195,17 @@ def fused_cv_supported(models, solver, tol=0):
         return False
     if spec.family != L.FAMILY_GEOMETRIC or spec.asian:
         return False
+    shape = (spec.dim, spec.m, spec.marks)
+    if shape not in ((1, 1, L.MARKS_NONE), (1, 1, L.MARKS_LOGNORMAL), (2, 2, L.MARKS_ICDF)):
+        return False
     if not FUSED_CV_ENABLED:
         return False
     nets = list(models) if isinstance(models, (list, tuple)) else [models]
     if len(nets) != (2 if solver.has_jumps else 1):
         return False
     keep = []
-    return all(_export_mlp(n, 'cpu', keep) is not None for n in nets)
+    outs = [spec.dim * spec.m, spec.dim]
+    return all(_export_mlp(n, 'cpu', keep, spec.dim + 1, o) is not None for n, o in zip(nets, outs))
 
 
 def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_out=False, dev_range=None):
@@ -210,8 +217,9 @@ def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_o
     nets = list(models) if isinstance(models, (list, tuple)) else [models]
     keep = []
     with torch.cuda.device(dev):
-        f = _export_mlp(nets[0], dev, keep)
-        g = _export_mlp(nets[1], dev, keep) if solver.has_jumps else None
+        d, m = solver.sde.dim, solver.sde.brown_dim // solver.sde.dim
+        f = _export_mlp(nets[0], dev, keep, d + 1, d * m)
+        g = _export_mlp(nets[1], dev, keep, d + 1, d) if solver.has_jumps else None
         rank, size = E.world()
         if dev_range is not None:
             lo, off, cnt = 0, 0, trials
@@ -227,11 +235,14 @@ def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_o
         inj = None
         if inject is not None:
             from .solvers import _as_dev_f32
-            z = _as_dev_f32(inject['z'], dev).reshape(trials, -1)
+            z = _as_dev_f32(inject['z'], dev)
+            K = int(z.shape[1])                  # (n, K[, dim]) unit normals of the correlated driver
+            z = z.reshape(trials, K, -1)
+            zc = _as_dev_f32(inject.get('zc'), dev)
             jt = _as_dev_f32(inject.get('jump_times'), dev)
             mk = _as_dev_f32(inject.get('marks'), dev)
-            keep += [z, jt, mk]
-            inj = L.SdemcInject(L.ptr(z), None, L.ptr(jt), L.ptr(mk), int(z.shape[1]), int(inject.get('total_steps', 0)))
+            keep += [z, zc, jt, mk]
+            inj = L.SdemcInject(L.ptr(z), L.ptr(zc), L.ptr(jt), L.ptr(mk), K, int(inject.get('total_steps', 0)))
         rng = L.SdemcRange(int(solver.seed), lo + off, cnt, dev_range.row_ptr() if dev_range is not None else None)
         L.check(lib.sdemc_mc_cv(sde, po, float(discounter.r), jm, f, g, rng, inj, L.ptr(mom.buf), L.ptr(gam),
                                 L.ptr(L.workspace(dev)), L.stream_ptr(dev)))

@@ -392,6 +392,49 @@ def cv_cases():
          mu=[0.02], sigma=[0.3], x0=[1.0], T=3.0, **{"f_" + k: v for k, v in mlp_weights(fd).items()})
 
 
+def cv_levy_cases():
+    """per-path gamma of apply_adapted_control_variates (varred.py:98-131) for the 2-D 'indep' exp-Levy SDE with the
+    nets of levy_rainbow_cv_experiment.py:39-40: f = Mlp(3, [50, 50, 50], 4), g = Mlp(3, [50, 50, 50], 2).  Own RNG,
+    so the section can be regenerated on its own."""
+    global RNG
+    keep, RNG = RNG, np.random.default_rng(20261018)
+    try:
+        torch.manual_seed(13)
+        f = ref.Mlp(3, [50, 50, 50], 4, batch_norm=False, batch_norm_init=False)
+        g = ref.Mlp(3, [50, 50, 50], 2, batch_norm=False, batch_norm_init=False)
+        eps = 0.05
+        levy = ref.ExpExampleLevy(1, 1, 0.5, 2, 0.02, 0.3, 0.2, eps, dim=2)
+        sde = ref.LevySde(levy, torch.tensor([1., 1.]))
+        csr = ref.ConstantShortRate(0.02)
+        opt = ref.Rainbow(1.0)
+        solver = ref.JumpEulerSolver(sde, 3, 10)
+        adam = torch.optim.Adam(list(f.parameters()) + list(g.parameters()))
+        dl = ref.simulate_adapted_data(1000, solver, opt, csr, bs=200)
+        ref.train_adapted_control_variates([f, g], adam, dl, solver, csr, 5, False)
+        f.eval(), g.eval()
+
+        solver = ref.JumpEulerSolver(sde, 3, 10)
+        bs = 24
+        K = 10 + solver.max_jumps
+        z, zc, jt, marks = jump_noise(bs, K, 2, solver.max_jumps, float(sde.jump_rate()), True, "icdf")
+        JumpInjector(solver, z, zc, jt, marks, "icdf")
+        dl = ref.simulate_adapted_data(bs, solver, opt, csr, bs=1, inference=True)
+        gammas = []
+        with torch.inference_mode():
+            for i in range(bs):
+                s, _ = ref.apply_adapted_control_variates([f, g], _ShapeProxy(dl.dataset, i), solver, csr)
+                gammas.append(float(s))
+        s_all, ss_all = ref.apply_adapted_control_variates([f, g], dl, solver, csr)
+        wf = {"f_" + k: v for k, v in mlp_weights(f).items()}
+        wg = {"g_" + k: v for k, v in mlp_weights(g).items()}
+        save("cv_levy_2d", z=z, zc=zc, jump_times=jt, marks=marks, cv_gamma=np.array(gammas, np.float32),
+             payoffs=dl.dataset.payoffs, total_steps=dl.dataset.total_steps, sum_gamma=float(s_all),
+             sumsq_gamma=float(ss_all), max_jumps=solver.max_jumps, disc_rate=0.02, eps=eps, x0=[1.0, 1.0], T=3.0,
+             jump_mean=float(sde.jump_mean()), rate=float(sde.jump_rate()), **wf, **wg)
+    finally:
+        RNG = keep
+
+
 class _ShapeProxy:
     """A one-sample 'DataLoader' over sample i of a reference dataset: iterates one batch of size 1 and exposes
     .dataset.paths / .batch_size the way varred.py:76,99 reads them."""
@@ -501,7 +544,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     for w in which:
         {"diffusion": diffusion_cases, "jump": jump_cases, "mlmc": mlmc_cases, "payoff": payoff_cases,
-         "cv": cv_cases, "estimator": estimator_cases, "seeded": seeded_cases}[w]()
+         "cv": cv_cases, "cv_levy": cv_levy_cases, "estimator": estimator_cases, "seeded": seeded_cases}[w]()
 
 
 def api_names():

@@ -19,8 +19,8 @@ DEV = "cuda"
 CV_ATOL = 5e-3
 
 
-def _net_from_golden(g, prefix):
-    net = sm.Mlp(2, [50, 50, 50], 1, batch_norm=False, batch_norm_init=False, device=DEV)
+def _net_from_golden(g, prefix, in_dim=2, out_dim=1):
+    net = sm.Mlp(in_dim, [50, 50, 50], out_dim, batch_norm=False, batch_norm_init=False, device=DEV)
     lin = [m for m in net.net if isinstance(m, torch.nn.Linear)]
     with torch.no_grad():
         for i, l in enumerate(lin):
@@ -47,6 +47,102 @@ def test_fused_cv_jump_gamma_vs_reference_golden():
     assert abs(m["sum"] - float(g["sum_gamma"])) < CV_ATOL * n
     # the plain payoff rides along in the control slot and is fp32-exact
     assert abs(m["sum_c"] - float(np.sum(g["payoffs"].astype(np.float64)))) < 1e-4
+
+
+def _bf16_emulated_gamma(g, solver, nets, payoff_kind):
+    """apply_adapted_control_variates (varred.py:98-131) on the oracle's trajectories of the golden's injected noise
+    with the precision of the fused kernel: weights, biases and hidden activations rounded to bf16, inputs as bf16
+    hi + lo pairs, fp32 accumulation"""
+    from common import oracle, oracle_sde
+    zc = g["zc"] if "zc" in g.files else None
+    osde = oracle_sde(solver)
+    res = oracle.jump(osde, g["z"], zc, g["jump_times"], g["marks"])
+    S = int(res["total_steps"])
+    n = res["paths"].shape[0]
+    bf = lambda v: v.to(torch.bfloat16).to(torch.float32)
+
+    def hilo(v):
+        hi = bf(v)
+        return hi + bf(v - hi)
+
+    def forward(net, inp):
+        lin = [m for m in net.net if isinstance(m, torch.nn.Linear)]
+        h = hilo(inp)
+        for i, l in enumerate(lin):
+            h = h @ bf(l.weight.detach().cpu()).t() + bf(l.bias.detach().cpu())
+            if i < 3:
+                h = bf(torch.relu(h))
+        return h
+
+    T = torch.as_tensor(res["times"][:, :S])
+    D = torch.exp(-T * 0.02)
+    P, Lf = torch.as_tensor(res["paths"][:, :S]), torch.as_tensor(res["left"][:, :S])
+    J = torch.as_tensor(res["jumps"][:, :S])
+    N = torch.as_tensor(res["normals"][:, :S]).reshape(n, S, -1)
+    fo = forward(nets[0], torch.cat([T.unsqueeze(-1), P], -1).reshape(n * S, -1)).reshape(n, S, -1)
+    go = forward(nets[1], torch.cat([T.unsqueeze(-1), Lf], -1).reshape(n * S, -1)).reshape(n, S, -1)
+    bcv = ((N * fo).sum(-1) * D).sum(-1)
+    jcv = (go * D.unsqueeze(-1) * J).sum(-1).sum(-1)
+    h = torch.diff(torch.as_tensor(res["times"][:, :S + 1]), dim=1)[:, :S - 1]
+    comp = (-float(solver.sde.jump_rate().sum()) * float(solver.sde.jump_mean()) * go[:, :S - 1] *
+            D[:, :S - 1].unsqueeze(-1) * h.unsqueeze(-1)).sum(-1).sum(-1)
+    last = res["paths"][np.arange(n), res["iters"]]
+    pay = oracle.payoff(oracle.payoff_struct(payoff_kind, 1.0), last) * np.float32(np.exp(-0.06))
+    return pay + (bcv + jcv + comp).numpy()
+
+
+def _levy_solver(eps, steps, **kw):
+    levy = sm.ExpExampleLevy(1, 1, 0.5, 2, 0.02, 0.3, 0.2, eps, dim=2)
+    return sm.JumpEulerSolver(sm.LevySde(levy, torch.tensor([1., 1.])), 3.0, steps, device=DEV, **kw)
+
+
+def test_fused_cv_levy_2d_gamma_vs_reference_golden():
+    """the configuration of levy_rainbow_cv_experiment.py:39-40 in the fused kernel: 2-D 'indep' exp-Levy SDE, rainbow
+    payoff, f = Mlp(3, [50, 50, 50], 4), g = Mlp(3, [50, 50, 50], 2); per-path gamma of the unmodified reference"""
+    g = golden("cv_levy_2d")
+    solver = _levy_solver(float(g["eps"]), int(g["z"].shape[1]) - int(g["max_jumps"]))
+    f, gnet = _net_from_golden(g, "f", 3, 4), _net_from_golden(g, "g", 3, 2)
+    assert sm.fused_cv_supported([f, gnet], solver)
+    n = g["z"].shape[0]
+    mom, gam = sm.mc_cv_fused([f, gnet], solver, n, sm.Rainbow(1.0), sm.ConstantShortRate(0.02),
+                              inject=dict(z=g["z"], zc=g["zc"], jump_times=g["jump_times"], marks=g["marks"],
+                                          total_steps=int(g["total_steps"])), gamma_out=True)
+    gam = gam.cpu().numpy()
+    m = mom.read()
+    err = np.max(np.abs(gam - g["cv_gamma"]))
+    # what the kernel's arithmetic should give: the reference's formula with bf16 weights / hidden activations and
+    # fp32 accumulation (the tensor-core precision), evaluated in PyTorch on the oracle's trajectories
+    emu = _bf16_emulated_gamma(g, solver, [f, gnet], 5)
+    err_emu = np.max(np.abs(gam - emu))
+    print("fused CV (Levy 2-D) over %d paths: max |gamma - ref fp32| = %.3e, max |gamma - bf16 emulation| = %.3e, "
+          "max |emulation - ref| = %.3e" % (n, err, err_emu, np.max(np.abs(emu - g["cv_gamma"]))))
+    assert err_emu < 2e-3                      # the kernel computes the reference's formula at tensor-core precision
+    assert err < 2e-2                          # ... whose distance to the fp32 reference is bf16 rounding: six outputs
+    assert abs(np.mean(gam - g["cv_gamma"])) < 4e-3     # x 57 iterations x marks up to |J| ~ 10; zero-mean, so unbiased
+    assert abs(m["sum"] - float(np.sum(gam.astype(np.float64)))) < 1e-4
+    assert abs(m["sum_c"] - float(np.sum(g["payoffs"].astype(np.float64)))) < 2e-4
+
+
+def test_fused_cv_levy_2d_unbiased_and_equal_to_the_stored_path_application():
+    """Philox-driven: (1) mc_apply_cvs takes the fused kernel for the Levy-rainbow nets, (2) its estimate agrees with
+    plain Monte Carlo (any adapted f, g is an unbiased control variate), (3) the variance of gamma equals that of
+    the PyTorch application of the same nets on stored trajectories within 10 % (bf16 weights / activations)"""
+    g = golden("cv_levy_2d")
+    f, gnet = _net_from_golden(g, "f", 3, 4), _net_from_golden(g, "g", 3, 2)
+    opt, csr = sm.Rainbow(1.0), sm.ConstantShortRate(0.02)
+    n = 400_000
+    solver = _levy_solver(0.05, 40, seed=5)
+    fused = sm.mc_apply_cvs([f, gnet], solver, n, opt, csr, sim_bs=10 ** 5, bs=2000)
+    plain = sm.mc_simple(4 * n, _levy_solver(0.05, 40, seed=6), opt, csr, bs=10 ** 5, payoff_time='adapted')
+    assert abs(fused.sample_mean - plain.sample_mean) < 4 * math.hypot(fused.sample_std, plain.sample_std)
+    from sde_mc_b200 import varred
+    varred.FUSED_CV_ENABLED = False
+    try:
+        stored = sm.mc_apply_cvs([f, gnet], _levy_solver(0.05, 40, seed=7), 40_000, opt, csr, sim_bs=20_000, bs=2000)
+    finally:
+        varred.FUSED_CV_ENABLED = True
+    var_fused, var_stored = fused.sample_std ** 2 * n, stored.sample_std ** 2 * 40_000
+    assert abs(var_fused / var_stored - 1.0) < 0.10, (var_fused, var_stored)
 
 
 def test_fused_cv_diffusion_gamma_vs_reference_golden():

@@ -130,6 +130,23 @@ def test_cv_gamma_jump_matches_reference():
     assert abs(float(gam.astype(np.float64).sum()) - float(g["sum_gamma"])) < 2e-4
 
 
+def test_cv_gamma_levy_2d_matches_reference():
+    """the 2-D 'indep' exp-Levy control variates of levy_rainbow_cv_experiment.py:39-40 (f: 4 outputs, one per driver
+    of every component; g: 2): per-path gamma of the unmodified reference on injected noise"""
+    g = golden("cv_levy_2d")
+    levy = sm.ExpExampleLevy(1, 1, 0.5, 2, 0.02, 0.3, 0.2, float(g["eps"]), dim=2)
+    sde = sm.LevySde(levy, t(g["x0"]))
+    solver = sm.JumpEulerSolver(sde, 3.0, int(g["z"].shape[1]) - int(g["max_jumps"]))
+    osde = oracle_sde(solver)
+    res = oracle.jump(osde, g["z"], g["zc"], g["jump_times"], g["marks"])
+    assert res["total_steps"] == int(g["total_steps"])
+    last = res["paths"][np.arange(len(res["iters"])), res["iters"]]
+    pay = oracle.payoff(oracle.payoff_struct(5, 1.0), last) * np.float32(np.exp(-0.02 * 3.0))
+    assert rel_err(pay, g["payoffs"], floor=1e-2) < 2e-5
+    gam = oracle.cv_gamma_jump(osde, res, pay, 0.02, float(g["jump_mean"]), _mlps(g, "f"), _mlps(g, "g"))
+    assert np.max(np.abs(gam - g["cv_gamma"])) < 5e-5
+
+
 def test_cv_gamma_diffusion_matches_reference():
     g = golden("cv_gbm_1d")
     solver = sm.EulerSolver(sm.Gbm(0.02, 0.3, t(g["x0"]), 1), 3.0, 16)
