@@ -78,24 +78,23 @@ OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0, "mlmc": 40.0}
 #   binding     : the busiest pipe of the capture and its thread-instructions per path-iteration and lanes per SM
 #   pipe_pct    : pipe utilisation in the capture (percent of peak while active)
 PROFILE = {
-    "gbm": dict(source="profiles/r01_ncu_gbm.summary.txt", capture_paths=1e8, dram_bytes=43264.0, inst=14.7,
+    "gbm": dict(source="profiles/r02_ncu_gbm.summary.txt", capture_paths=1e8, dram_bytes=20224.0, inst=14.59,
                 binding=dict(pipe="xu", inst=2.02, lanes_per_sm=16),
-                pipe_pct=dict(issue=65.5, fma=32.0, alu=44.9, xu=72.2)),
-    "merton": dict(source="profiles/r01_ncu_merton.summary.txt", capture_paths=5e7, dram_bytes=30208.0, inst=39.7,
-                   binding=dict(pipe="issue", inst=39.7, lanes_per_sm=128),
-                   pipe_pct=dict(issue=68.2, fma=30.6, alu=48.1, xu=42.7)),
-    "levy2d": dict(source="profiles/r01_ncu_levy2d.summary.txt", capture_paths=5e6, dram_bytes=371456.0, inst=None,
-                   binding=None, pipe_pct=dict(issue=66.4, fma=31.9, alu=46.3, xu=47.0)),
-    "merton_cv": dict(source="profiles/r01_ncu_merton_cv.summary.txt", capture_paths=2e6, dram_bytes=165120.0, inst=None,
-                      binding=None, pipe_pct=dict(issue=44.5, fma=5.7, alu=45.5, xu=6.3, tensor=42.4)),
-    "mlmc": dict(source="profiles/r01_ncu_mlmc.summary.txt", capture_paths=None, dram_bytes=15616.0, inst=None,
-                 binding=None, pipe_pct=dict(issue=69.0, fma=26.4, alu=56.2, xu=47.2)),
-    "gbm_store": dict(source="profiles/r01_ncu_gbm_store.summary.txt", capture_paths=4e6,
-                      dram_bytes=8.128509e9 + 1.26625e8, inst=None, binding=None,
-                      pipe_pct=dict(issue=37.3, fma=16.7, alu=24.6, xu=21.6)),
-    "merton_store": dict(source="profiles/r01_ncu_merton_store.summary.txt", capture_paths=2e6,
-                         dram_bytes=5.394213e9 + 3.1638e8, inst=None, binding=None,
-                         pipe_pct=dict(issue=48.2, fma=15.3, alu=28.0, xu=9.4)),
+                pipe_pct=dict(issue=65.6, fma=32.0, alu=45.0, xu=72.3)),
+    "merton": dict(source="profiles/r02_ncu_merton.summary.txt", capture_paths=5e7, dram_bytes=45568.0, inst=37.36,
+                   binding=dict(pipe="issue", inst=37.36, lanes_per_sm=128),
+                   pipe_pct=dict(issue=69.0, fma=34.0, alu=39.9, xu=45.6)),
+    "levy2d": dict(source="profiles/r02_ncu_levy2d.summary.txt", capture_paths=5e6, dram_bytes=36608.0, inst=145.3,
+                   binding=dict(pipe="issue", inst=145.3, lanes_per_sm=128),
+                   pipe_pct=dict(issue=65.6, fma=31.7, alu=45.9, xu=46.2)),
+    "merton_cv": dict(source="profiles/r02_ncu_merton_cv.summary.txt", capture_paths=2e6, dram_bytes=139520.0,
+                      inst=667.7, binding=None, pipe_pct=dict(issue=43.7, fma=5.6, alu=44.8, xu=6.2, tensor=41.9)),
+    "mlmc": dict(source="profiles/r02_ncu_mlmc.summary.txt", capture_paths=None, dram_bytes=15104.0, inst=None,
+                 binding=None, pipe_pct=dict(issue=68.5, fma=26.2, alu=55.0, xu=44.0)),
+    "gbm_store": dict(source="profiles/r02_ncu_gbm_store.summary.txt", capture_paths=4e6, dram_bytes=8.25387e9,
+                      inst=None, binding=None, pipe_pct=dict(issue=37.6, fma=16.4, alu=25.9, xu=21.8)),
+    "merton_store": dict(source="profiles/r02_ncu_merton_store.summary.txt", capture_paths=2e6, dram_bytes=5.71235e9,
+                         inst=None, binding=None, pipe_pct=dict(issue=48.5, fma=15.2, alu=28.7, xu=9.4)),
 }
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 

@@ -52,13 +52,36 @@ def _coeffs_f64(solver, payoff=None, df=1.0):
     return c
 
 
-def _level_moments(solver, payoff, discounter, trials, fine, coarse, buf=None, dev_range=None, reduce=True):
+class _LevelContext:
+    """what every level launch of one estimator call shares: the library, the payoff / coefficient structs and a
+    template of the SDE struct (only num_steps changes from level to level).  Built once per call: at 8 GPUs a whole
+    MLMC pass is ~1 ms of device time, and rebuilding these structs per level (kernel_spec, tensor -> float
+    conversions) cost about as much on the host."""
+
+    def __init__(self, solver, payoff, discounter):
+        self.dev = solver._compute_device()
+        self.lib = _pair_lib(solver)
+        self.df = float(discounter(solver.time_interval))
+        self.po = _spec.payoff_struct(payoff, self.df, L.INDEX_ADAPTED)
+        self.sde0 = solver._sde_struct(1)
+        self.use64 = _wants_fp64(solver)
+        self.coeffs64 = _coeffs_f64(solver, payoff, self.df) if self.use64 else None
+        self.seed = int(solver.seed)
+        self.rank, self.size = E.world()
+
+    def sde(self, fine):
+        s = L.SdemcSde.from_buffer_copy(self.sde0)
+        s.num_steps = int(fine)
+        return s
+
+
+def _level_moments(solver, payoff, discounter, trials, fine, coarse, buf=None, dev_range=None, reduce=True, ctx=None):
     """moments of D(T) (P(fine) - P(coarse)) over `trials` coupled pairs (coarse == 0: single level), accumulated
     into `buf` (a row of the estimator's (levels, 8) tensor) or a fresh Moments.  dev_range = (DeviceRange, row): the
     kernel reads this level's path range from device memory (run_mlmc)."""
-    dev = solver._compute_device()
-    lib = _pair_lib(solver)
-    rank, size = E.world()
+    if ctx is None:
+        ctx = _LevelContext(solver, payoff, discounter)
+    dev, lib, rank, size = ctx.dev, ctx.lib, ctx.rank, ctx.size
     if dev_range is not None:
         lo, off, cnt = 0, 0, int(trials or 0)
         d_range = dev_range[0].row_ptr(dev_range[1])
@@ -67,18 +90,17 @@ def _level_moments(solver, payoff, discounter, trials, fine, coarse, buf=None, d
         lo = solver._take_paths(trials)
         off, cnt = E.shard(trials, rank, size)
         d_range = None
-    df = float(discounter(solver.time_interval))
-    po = _spec.payoff_struct(payoff, df, L.INDEX_ADAPTED)
-    sde = solver._sde_struct(fine)
+    sde, po = ctx.sde(fine), ctx.po
     with torch.cuda.device(dev):
         mom = E.Moments(dev, buf)
-        rng = L.SdemcRange(int(solver.seed), lo + off, cnt, d_range)
-        if _wants_fp64(solver) and coarse > 0:
-            L.check(lib.sdemc_mlmc_pair_f64(sde, _coeffs_f64(solver, payoff, df), po, int(fine), int(coarse), rng, None,
-                                            L.ptr(mom.buf), None, L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+        rng = L.SdemcRange(ctx.seed, lo + off, cnt, d_range)
+        ws = L.ptr(L.workspace(dev))          # one workspace per stream: the levels run on streams of their own
+        if ctx.use64 and coarse > 0:
+            L.check(lib.sdemc_mlmc_pair_f64(sde, ctx.coeffs64, po, int(fine), int(coarse), rng, None,
+                                            L.ptr(mom.buf), None, ws, L.stream_ptr(dev)))
         else:
             L.check(lib.sdemc_mlmc_pair(sde, po, int(fine), int(coarse), rng, None, L.ptr(mom.buf), None,
-                                        L.ptr(L.workspace(dev)), L.stream_ptr(dev)))
+                                        ws, L.stream_ptr(dev)))
         if reduce:
             mom.all_reduce()
     return mom
@@ -113,13 +135,14 @@ def _all_levels(solver, payoff, discounter, trials, levels, plan=None):
     trials = [trials] * len(levels) if not isinstance(trials, (list, tuple)) else trials
     dev = solver._compute_device()
     coarse = [0] + list(levels[:-1])
+    ctx = _LevelContext(solver, payoff, discounter)
     with torch.cuda.device(dev):
         out = LevelMoments(dev, len(levels))
         rows = [out.buf[i] for i in range(len(levels))]
         dr = [(plan, i) if plan is not None else None for i in range(len(levels))]
         if os.environ.get("SDEMC_MLMC_STREAMS", "1") == "0" or len(levels) < 2:
             for n, f, c, row, d in zip(trials, levels, coarse, rows, dr):
-                _level_moments(solver, payoff, discounter, n, f, c, row, d, reduce=False)
+                _level_moments(solver, payoff, discounter, n, f, c, row, d, reduce=False, ctx=ctx)
             return out.all_reduce()
         pool = _level_streams.setdefault(dev, [])
         while len(pool) < len(levels):
@@ -130,7 +153,7 @@ def _all_levels(solver, payoff, discounter, trials, levels, plan=None):
         for side, n, f, c, row, d in zip(pool, trials, levels, coarse, rows, dr):
             side.wait_event(fork)
             with torch.cuda.stream(side):
-                _level_moments(solver, payoff, discounter, n, f, c, row, d, reduce=False)
+                _level_moments(solver, payoff, discounter, n, f, c, row, d, reduce=False, ctx=ctx)
             join = torch.cuda.Event()
             join.record(side)
             cur.wait_event(join)

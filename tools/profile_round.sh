@@ -18,9 +18,9 @@ except Exception as e:
 PY
 done
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_${tag}_reference.json 2>/dev/null
-# launch list of the default bench command (cold-cache, serialised: shares, not absolutes)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_gbm.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_gbm.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_merton.csv python bench.py --workload merton --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_merton.log 2>&1
+# launch list of the default bench command = the Merton north-star workload (cold-cache, serialised: shares, not absolutes)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_merton.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_merton.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_gbm.csv python bench.py --workload gbm --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_gbm.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_merton_store.csv python bench.py --workload merton_store --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_merton_store.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_mlmc.csv python bench.py --workload mlmc --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_mlmc.log 2>&1
 prof() { # workload kernel-regex paths
@@ -34,7 +34,7 @@ prof() { # workload kernel-regex paths
 prof gbm diffusion_kernel 1e8
 prof merton jump1d_kernel 5e7
 prof levy2d jump_kernel 5e6
-prof mlmc jump_flat_kernel 1
+prof mlmc jump_flat1d_kernel 1
 prof merton_cv cv_kernel 2e6
 prof gbm_store diffusion_store_tma_kernel 4e6
 prof merton_store jump_kernel 2e6
