@@ -33,9 +33,23 @@ static_assert(kTmaTileElems == 32 || kTmaTileElems == 16, "tile rows of 128 or 6
 constexpr int kTmaTileBytes = 32 * kTmaTileElems * 4;
 
 __device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, uint32_t smem, int col, int row) {
+#if defined(SDEMC_EXP_TMA_HINT)   // (experiment) L2 eviction policy for the written lines: 1 evict_first, 2 evict_last, 3 no_allocate... 
+  uint64_t pol;
+#if SDEMC_EXP_TMA_HINT == 1
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#elif SDEMC_EXP_TMA_HINT == 2
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#else
+  asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map), "r"(col),
+               "r"(row), "r"(smem), "l"(pol)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col),
                "r"(row), "r"(smem)
                : "memory");
+#endif
 }
 
 // One output array of one warp: two swizzled tiles, filled four elements at a time, flushed through TMA.

@@ -5,6 +5,9 @@
 #include "diffusion_tma.cuh"
 #include "launch.cuh"
 
+#ifndef SDEMC_EXP_L2PROMO
+#define SDEMC_EXP_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_NONE
+#endif
 namespace sdemc {
 namespace {
 
@@ -31,8 +34,14 @@ bool make_row_map(CUtensorMap* map, float* base, uint64_t n_rows, uint64_t row_l
   const cuuint32_t box[2] = {kTmaTileElems, 32};
   const cuuint32_t estr[2] = {1, 1};
   return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                kTmaTileElems == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+                kTmaTileElems == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, SDEMC_EXP_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
          CUDA_SUCCESS;
+}
+
+// row length the tensor map declares: the pitch when the rows are padded to whole tiles (the padding belongs to the
+// allocation, sdemc_paths_out), else the row itself
+inline uint64_t tma_map_row_len(uint64_t row_len, uint64_t pitch) {
+  return (pitch >= row_len && pitch % kTmaTileElems == 0) ? pitch : row_len;
 }
 
 inline bool tma_rows_ok(const float* base, uint64_t pitch) {
@@ -48,8 +57,15 @@ int run_store_tma(const LaunchArgs& a) {
   if (a.no_tma) return 1;
   CUtensorMap mp, mn;
   const uint64_t S = (uint64_t)a.sde.num_steps;
-  if (!make_row_map(&mp, a.out.paths, a.range.n_paths, (S + 1) * C::DIM, a.out.pitch_state)) return 1;
-  if (!make_row_map(&mn, a.out.normals, a.range.n_paths, S * NPS, a.out.pitch_normals)) return 1;
+#ifdef SDEMC_TMA_CLIP_AT_ROW_END
+  const uint64_t len_p = (S + 1) * C::DIM, len_n = S * NPS;
+#else
+  // The maps span the whole pitch, not just the row: a box the tensor bound cuts inside a row costs the engine
+  // several times a full box (measured), so the last tile of a row spills into the row's padding
+  const uint64_t len_p = tma_map_row_len((S + 1) * C::DIM, a.out.pitch_state), len_n = tma_map_row_len(S * NPS, a.out.pitch_normals);
+#endif
+  if (!make_row_map(&mp, a.out.paths, a.range.n_paths, len_p, a.out.pitch_state)) return 1;
+  if (!make_row_map(&mn, a.out.normals, a.range.n_paths, len_n, a.out.pitch_normals)) return 1;
   auto kernel = diffusion_store_tma_kernel<C, HESTON, INJECT>;
   const size_t smem = (size_t)(kTmaStoreBlock / 32) * 4 * kTmaTileBytes + 1024;
   SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

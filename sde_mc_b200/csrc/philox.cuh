@@ -39,8 +39,11 @@ __host__ inline PhiloxKeys make_philox_keys(uint64_t seed) {
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKeys& K, uint32_t (&o)[4]) {
+#ifndef SDEMC_EXP_PHILOX_ROUNDS   // (timing experiments only)
+#define SDEMC_EXP_PHILOX_ROUNDS 10
+#endif
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < SDEMC_EXP_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)c0 * 0xD2511F53u;
     const uint64_t p1 = (uint64_t)c2 * 0xCD9E8D57u;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r];
