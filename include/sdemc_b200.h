@@ -194,7 +194,9 @@ typedef struct {
  * S = num_steps for the diffusion solver, num_steps + max_jumps for the jump solver.  NULL = skip.
  * Rows (one per path) may be padded: pitch_* = floats between consecutive rows, 0 = dense (the reference's
  * contiguous layout).  With a pitch that is a multiple of 4 floats and 16-byte aligned bases the kernels write
- * 16-byte vectors covering whole 128-byte lines; any other pitch takes the 4-byte store path. */
+ * 16-byte vectors covering whole 128-byte lines; any other pitch takes the 4-byte store path.  The padding between
+ * the end of a row and its pitch belongs to the library: its contents after a call are unspecified (the TMA kernel
+ * writes whole 128-byte tiles into it rather than have the tensor bound cut a tile inside a row). */
 typedef struct {
   uint32_t struct_size; /* sizeof(sdemc_paths_out) */
   uint32_t flags;       /* SDEMC_OUT_* */

@@ -3,9 +3,11 @@
 // Same contract and arithmetic as diffusion_kernel<.., STORE=true> (DiffusionSolver.solve solvers.py:68-88: paths
 // (bs, S+1, dim) and increments (bs, S, dim[, m]), row-per-path), different data path.  The 16-byte-store flush of
 // store_tile.cuh drains through the LSU queue it shares with the staging STS/LDS and does not overlap the step
-// loop (measured: 1.57 ms of compute + 1.2 ms of stores for 8 GB).  Measured here: 2.39 ms
-// against 2.82 ms for the same 8 GB (3.4 TB/s); 1.35 ms with the bulk copy left out.  The engine alone moves these
-// boxes at 5.4-5.6 TB/s (tools/tma_box_probe.cu), so copy and step loop hardly overlap yet.
+// loop (2.82 ms for the 8 GB of a 4e6 x 252 GBM solve()).  Through TMA: 1.73 ms (4.7 TB/s, 0.72 of the measured copy
+// bandwidth); with the step arithmetic stubbed out 1.66 ms -- what remains is how fast 128-byte pieces scattered over
+// ~57 000 open rows reach HBM (per-thread 32-byte stores hit the same ~4.8 TB/s, tools/thread_row_store_probe.cu),
+// not the step loop.  The tensor maps declare the whole PITCH as the row length: a box cut by the tensor bound
+// inside a row costs the engine several full boxes (2.31 ms with maps that end at the row).
 // Here every warp keeps a
 // [32 paths][32 elements] tile per output array in shared memory in the layout TMA reads (128-byte rows, 128B
 // swizzle), fills it with 16-byte vector stores -- four consecutive elements of a path are collected in registers;
@@ -14,8 +16,9 @@
 // address arithmetic, nothing in the LSU but the staging stores; tiles are double buffered and reused after
 // cp.async.bulk.wait_group.read.  Rows past the end of the call and columns past the end of a row are clipped by
 // the tensor map's bounds, so the kernel has no tail paths: it runs whole super-groups of steps and lets TMA drop
-// what does not exist.  Requires a row pitch that is a multiple of 16 bytes and 16-byte aligned bases (the Python
-// layer pads the pitch to 128 bytes); launch_diffusion.cu falls back to the store_tile.cuh kernel otherwise.
+// what does not exist; columns between the end of a row and its pitch (the caller's padding) receive the surplus of
+// the last tile.  Requires a row pitch that is a multiple of 16 bytes and 16-byte aligned bases (the Python layer
+// pads the pitch to 128 bytes); launch_diffusion.cu falls back to the store_tile.cuh kernel otherwise.
 #pragma once
 #include <cuda.h>
 
@@ -33,23 +36,9 @@ static_assert(kTmaTileElems == 32 || kTmaTileElems == 16, "tile rows of 128 or 6
 constexpr int kTmaTileBytes = 32 * kTmaTileElems * 4;
 
 __device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, uint32_t smem, int col, int row) {
-#if defined(SDEMC_EXP_TMA_HINT)   // (experiment) L2 eviction policy for the written lines: 1 evict_first, 2 evict_last, 3 no_allocate... 
-  uint64_t pol;
-#if SDEMC_EXP_TMA_HINT == 1
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-#elif SDEMC_EXP_TMA_HINT == 2
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-#else
-  asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
-#endif
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map), "r"(col),
-               "r"(row), "r"(smem), "l"(pol)
-               : "memory");
-#else
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(col),
                "r"(row), "r"(smem)
                : "memory");
-#endif
 }
 
 // One output array of one warp: two swizzled tiles, filled four elements at a time, flushed through TMA.

@@ -5,9 +5,6 @@
 #include "diffusion_tma.cuh"
 #include "launch.cuh"
 
-#ifndef SDEMC_EXP_L2PROMO
-#define SDEMC_EXP_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_NONE
-#endif
 namespace sdemc {
 namespace {
 
@@ -34,7 +31,7 @@ bool make_row_map(CUtensorMap* map, float* base, uint64_t n_rows, uint64_t row_l
   const cuuint32_t box[2] = {kTmaTileElems, 32};
   const cuuint32_t estr[2] = {1, 1};
   return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                kTmaTileElems == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, SDEMC_EXP_L2PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+                kTmaTileElems == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
          CUDA_SUCCESS;
 }
 

@@ -82,10 +82,10 @@ int main() {
   cudaMalloc(&sink, 4);
   const size_t smem = 4 * 16384 + 1024;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  for (int stage : {0, 1})
+  for (int stage : {1})
   for (int two : {1}) {
-    for (int C : {1, 2}) {
-      for (int delay : {0, 400, 800}) {
+    for (int C : {1, 2, 4, 8}) {
+      for (int delay : {0, 400, 600}) {
         const int R = 32 / C;
         CUtensorMap mA, mB;
         if (!make_map(&mA, dA, n_rows, row_len, pitch, C, R) || !make_map(&mB, dB, n_rows, row_len, pitch, C, R)) continue;
