@@ -149,15 +149,18 @@ typedef struct {
   uint64_t n_paths;
 } sdemc_dev_range;
 
+#define SDEMC_RANGE_COUNT_ON_HOST 1u /* with d_range: n_paths below is exact; only path_lo is taken from *d_range */
 typedef struct {
   uint32_t struct_size; /* sizeof(sdemc_range) */
-  uint32_t reserved;
+  uint32_t flags;       /* SDEMC_RANGE_* */
   uint64_t seed;
   uint64_t path_lo;    /* first global path id of this call */
   uint64_t n_paths;    /* number of paths in this call */
   /* NULL, or a device pointer: the kernels then take (path_lo, n_paths) from *d_range when they RUN, and the two host
    * fields above only bound the grid (n_paths = 0: unknown, a full persistent grid).  Moments entry points only
-   * (sdemc_mc_moments, sdemc_mlmc_pair, sdemc_mc_cv), without injected noise or per-path outputs. */
+   * (sdemc_mc_moments, sdemc_mlmc_pair, sdemc_mc_cv), without injected noise or per-path outputs.
+   * SDEMC_RANGE_COUNT_ON_HOST: the caller knows the count and (*d_range).n_paths equals n_paths; what lives on the
+   * device is only WHERE the ids start -- a launch captured in a CUDA graph and replayed on new path ids. */
   const sdemc_dev_range* d_range;
 } sdemc_range;
 

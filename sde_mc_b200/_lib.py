@@ -26,6 +26,7 @@ INDEX_TERMINAL, INDEX_ADAPTED = 0, 1
 DRAWS_BROWNIAN, DRAWS_QUEUE, DRAWS_INLINE, DRAWS_PACKED = range(4)
 SHORT_AUTO, SHORT_OFF, SHORT_ALIGNED, SHORT_PACKED, SHORT_PACKED_GENERIC = range(5)
 OUT_NO_TMA = 1
+RANGE_COUNT_ON_HOST = 1
 
 
 class _Sized(C.Structure):
@@ -57,11 +58,11 @@ class SdemcPayoff(_Sized):
 class SdemcRange(_Sized):
     """SdemcRange(seed, path_lo, n_paths[, d_range]); d_range: device pointer to a (path_lo, n_paths) pair of uint64
     written by sdemc_plan_mc / sdemc_plan_mlmc -- the kernels then read their range when they run"""
-    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("seed", C.c_uint64), ("path_lo", C.c_uint64),
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64), ("path_lo", C.c_uint64),
                 ("n_paths", C.c_uint64), ("d_range", C.c_void_p)]
 
-    def __init__(self, seed=0, path_lo=0, n_paths=0, d_range=None):
-        super().__init__(0, seed, path_lo, n_paths, d_range)
+    def __init__(self, seed=0, path_lo=0, n_paths=0, d_range=None, flags=0):
+        super().__init__(flags, seed, path_lo, n_paths, d_range)
 
 
 class SdemcInject(_Sized):

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256, diffusion_min_blocks<C, HESTON, INJECT, S
   constexpr int NBUF = BPS * kNormalsPerBlock;
   constexpr bool FAST1D = DIM == 1 && M == 1 && !HESTON && !INJECT && !STORE && C::FAMILY != SDEMC_FAMILY_USER;
   const int S = s.num_steps;
+  range_stage<RMODE>(rg);
 
   extern __shared__ float diff_store_smem[];  // STORE: two staging tiles per warp (paths, increments)
   using Writer = DiffusionStoreWriter<C>;

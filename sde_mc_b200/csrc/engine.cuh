@@ -48,6 +48,7 @@ struct DevPayoff {
 struct DevRange {
   uint64_t path_lo, n_paths;
   const uint64_t* dyn;  // device-resident {path_lo, n_paths} overriding the two above (sdemc_range.d_range), or nullptr
+  bool count_on_host;   // with dyn: n_paths above is exact, only path_lo comes from device memory (SDEMC_RANGE_COUNT_ON_HOST)
 };
 // The range a moments kernel works on.  With `dyn` set it is read from device memory at run time: the launch was
 // queued before the range was known (pilot -> size the run -> run without a host read in between, mc.py:418-440,
@@ -64,11 +65,28 @@ __device__ __forceinline__ uint64_t range_lo(const DevRange& rg) { return rg.dyn
 // registers are measurable: the 1-D uniform-grid kernel sits at its register limit (the run-time form cost 3 % of the
 // C2 throughput: 1.608e12 vs 1.659e12) and the short-path kernels spend ~340 instructions on a whole path (3 % of an
 // MLMC pass).  RANGE_HOST: the constant-bank reads these kernels always had; RANGE_DEVICE: device memory.
-enum { RANGE_HOST = 0, RANGE_DEVICE = 1 };
+// RANGE_LO_DEVICE: only the first path id comes from device memory, the count is the launch parameter (a captured
+// launch replayed on new path ids): loop control keeps its constant-bank operand -- with the count loaded from memory
+// ptxas compiles the persistent-lane loop of jump_flat1d_kernel into 1360 instructions instead of 800 (+6 % run time).
+enum { RANGE_HOST = 0, RANGE_DEVICE = 1, RANGE_LO_DEVICE = 2 };
+// RANGE_DEVICE: the CTA copies the two words into shared memory once (range_stage, first statement of the kernel) and
+// every path reads them back with a volatile LDS: a fresh global load at the start of every path sat on the critical
+// path of the persistent-lane kernels (MLMC level 0: 4.59 ms against 4.26 ms with a host range).
+__shared__ uint64_t g_sh_range[2];
 template <int MODE>
-__device__ __forceinline__ uint64_t range_n(const DevRange& rg) { return MODE == RANGE_DEVICE ? range_dyn_word(rg, 1) : rg.n_paths; }
+__device__ __forceinline__ void range_stage(const DevRange& rg) {
+  if (MODE != RANGE_HOST) {
+    if (threadIdx.x < 2) g_sh_range[threadIdx.x] = range_dyn_word(rg, (int)threadIdx.x);
+    __syncthreads();
+  }
+}
+// a plain shared read, not volatile asm: inside the divergent persistent-lane loop a volatile access pins the control
+// flow around it (no predication of the path restart; 1360 instead of 800 instructions in jump_flat1d_kernel)
+__device__ __forceinline__ uint64_t range_staged_word(int w) { return g_sh_range[w]; }
 template <int MODE>
-__device__ __forceinline__ uint64_t range_lo(const DevRange& rg) { return MODE == RANGE_DEVICE ? range_dyn_word(rg, 0) : rg.path_lo; }
+__device__ __forceinline__ uint64_t range_n(const DevRange& rg) { return MODE == RANGE_DEVICE ? range_staged_word(1) : rg.n_paths; }
+template <int MODE>
+__device__ __forceinline__ uint64_t range_lo(const DevRange& rg) { return MODE != RANGE_HOST ? range_staged_word(0) : rg.path_lo; }
 
 struct DevInject {
   const float* z;

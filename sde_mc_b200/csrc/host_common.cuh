@@ -119,6 +119,7 @@ inline DevRange to_dev(const sdemc_range& r) {
   d.path_lo = r.path_lo;
   d.n_paths = r.n_paths;
   d.dyn = reinterpret_cast<const uint64_t*>(r.d_range);
+  d.count_on_host = d.dyn != nullptr && (r.flags & SDEMC_RANGE_COUNT_ON_HOST) != 0 && r.n_paths > 0;
   if (d.dyn && d.n_paths == 0) d.n_paths = ~0ull >> 1;
   return d;
 }

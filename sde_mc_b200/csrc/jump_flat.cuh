@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256, 3)
   constexpr int BPS = blocks_per_group(NZ);
   constexpr int NBUF = BPS * kNormalsPerBlock;
   using Src = InlineJumps<MARKS>;
+  range_stage<RMODE>(rg);
 
   Accum acc;
   acc.zero();
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(256, 3)
   static_assert(C::DIM == 1 && C::M == 1 && !C::ASIAN && C::MARKS == SDEMC_MARKS_LOGNORMAL, "1-D lognormal-mark models");
   static_assert(!FAST || C::FAMILY == SDEMC_FAMILY_GEOMETRIC, "the restated iteration is the geometric Euler step");
   using Src = PackedJumps<C::MARKS>;
+  range_stage<RMODE>(rg);
   Accum acc;
   acc.zero();
   const int n = s.num_steps;

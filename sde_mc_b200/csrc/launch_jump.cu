@@ -79,6 +79,7 @@ int run_flat(const LaunchArgs& a) {
 template <class C, bool FAST>
 int run_flat1d(const LaunchArgs& a) {
   if (per_path_of_out(a.out).any()) return launch_flat(jump_flat1d_kernel<C, FAST, true, RANGE_HOST>, a);
+  if (a.range.dyn && a.range.count_on_host) return launch_flat(jump_flat1d_kernel<C, FAST, false, RANGE_LO_DEVICE>, a);
   if (a.range.dyn) return launch_flat(jump_flat1d_kernel<C, FAST, false, RANGE_DEVICE>, a);
   return launch_flat(jump_flat1d_kernel<C, FAST, false, RANGE_HOST>, a);
 }

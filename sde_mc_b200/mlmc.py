@@ -75,7 +75,8 @@ class _LevelContext:
         return s
 
 
-def _level_moments(solver, payoff, discounter, trials, fine, coarse, buf=None, dev_range=None, reduce=True, ctx=None):
+def _level_moments(solver, payoff, discounter, trials, fine, coarse, buf=None, dev_range=None, reduce=True, ctx=None,
+                   count_on_host=False):
     """moments of D(T) (P(fine) - P(coarse)) over `trials` coupled pairs (coarse == 0: single level), accumulated
     into `buf` (a row of the estimator's (levels, 8) tensor) or a fresh Moments.  dev_range = (DeviceRange, row): the
     kernel reads this level's path range from device memory (run_mlmc)."""
@@ -93,7 +94,9 @@ def _level_moments(solver, payoff, discounter, trials, fine, coarse, buf=None, d
     sde, po = ctx.sde(fine), ctx.po
     with torch.cuda.device(dev):
         mom = E.Moments(dev, buf)
-        rng = L.SdemcRange(ctx.seed, lo + off, cnt, d_range)
+        # count_on_host: `cnt` is exact and only the first path id is read from device memory (graph replays)
+        rng = L.SdemcRange(ctx.seed, lo + off, cnt, d_range,
+                           L.RANGE_COUNT_ON_HOST if (count_on_host and d_range is not None and cnt > 0) else 0)
         ws = L.ptr(L.workspace(dev))          # one workspace per stream: the levels run on streams of their own
         if ctx.use64 and coarse > 0:
             L.check(lib.sdemc_mlmc_pair_f64(sde, ctx.coeffs64, po, int(fine), int(coarse), rng, None,
@@ -125,22 +128,100 @@ class LevelMoments:
         return [dict(zip(L.MOMENT_FIELDS, row)) for row in self.buf.tolist()]
 
 
+class _GraphedPass:
+    """One MLMC pass (zero the moments, fork, one launch per level on its own stream, join) captured ONCE as a CUDA
+    graph and replayed (opt-in, see GRAPH_LEVELS: measured no faster than queueing the launches).  The kernels read their
+    path ranges from device memory (sdemc_range.d_range, the run_mlmc mechanism), so a replay only needs the 16 bytes
+    per level that say which global path ids this call simulates."""
+
+    def __init__(self, solver, payoff, discounter, counts, levels, ctx):
+        dev = ctx.dev
+        self.buf = torch.zeros((len(levels), L.NUM_MOMENTS), dtype=torch.float64, device=dev)
+        self.plan = E.DeviceRange(dev, len(levels))
+        warm = torch.cuda.Stream(device=dev)           # capture must not start on the legacy default stream
+        warm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(warm):
+            _queue_levels(solver, payoff, discounter, counts, levels, ctx, self.buf, self.plan)   # allocates workspaces
+        torch.cuda.current_stream(dev).wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.buf.zero_()
+            _queue_levels(solver, payoff, discounter, counts, levels, ctx, self.buf, self.plan)
+
+    def run(self, ranges):
+        """ranges: [(first global path id of this rank's share, count)] per level"""
+        host = torch.tensor(ranges, dtype=torch.int64).pin_memory()
+        self.plan.ranges.copy_(host, non_blocking=True)
+        self.graph.replay()
+        out = LevelMoments.__new__(LevelMoments)
+        out.buf = self.buf.clone()                     # the static tensor is rewritten by the next replay
+        return out
+
+
+_graphs = {}
+import os as _os
+# Opt-in (SDEMC_MLMC_GRAPH=1 or mlmc.GRAPH_LEVELS = True): mc_multilevel / get_optimal_trials replay a captured pass.
+# Measured on B200 (C5 pass, ms): 1 GPU 5.84 graph / 5.56 queued launches (the graph's branches overlap less than
+# eight streams do), 2 GPUs 3.01 / 2.89, 4 GPUs 1.58 / 1.54, 8 GPUs 0.86 / 0.86 -- queueing from Python is not what
+# bounds a pass once the per-call context is built once (_LevelContext), so the default stays with the streams.
+GRAPH_LEVELS = _os.environ.get("SDEMC_MLMC_GRAPH", "0") == "1"
+
+
+def _queue_levels(solver, payoff, discounter, counts, levels, ctx, buf, plan):
+    """one launch per level into the rows of `buf`, each on a stream of its own forked from and joined back into the
+    current stream; every kernel takes its path range from row l of `plan` (counts only bound the grids)"""
+    dev = ctx.dev
+    coarse = [0] + list(levels[:-1])
+    pool = _level_streams.setdefault(dev, [])
+    while len(pool) < len(levels):
+        pool.append(torch.cuda.Stream(device=dev))
+    cur = torch.cuda.current_stream(dev)
+    fork = torch.cuda.Event()
+    fork.record(cur)
+    for i, (side, n, f, c) in enumerate(zip(pool, counts, levels, coarse)):
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            _level_moments(solver, payoff, discounter, n, f, c, buf[i], (plan, i), reduce=False, ctx=ctx,
+                           count_on_host=True)
+        join = torch.cuda.Event()
+        join.record(side)
+        cur.wait_event(join)
+
+
 def _all_levels(solver, payoff, discounter, trials, levels, plan=None):
     """Queue one launch per level into the rows of one LevelMoments and all-reduce it ONCE.  The levels are
     independent, so each goes to a stream of its own (forked from and joined back into the current stream): level 0
     fills the GPU first, the small fine levels -- a wave or two of long serial paths each -- then overlap instead of
     running their tails one after the other.  SDEMC_MLMC_STREAMS=0 keeps everything on the current stream.
-    plan: an E.DeviceRange with one row per level (run_mlmc) -- the kernels read their ranges from device memory."""
+    plan: an E.DeviceRange with one row per level (run_mlmc) -- the kernels read their ranges from device memory.
+    Host-known trial counts (mc_multilevel, get_optimal_trials) replay a captured CUDA graph of the same launches."""
     import os
     trials = [trials] * len(levels) if not isinstance(trials, (list, tuple)) else trials
     dev = solver._compute_device()
     coarse = [0] + list(levels[:-1])
     ctx = _LevelContext(solver, payoff, discounter)
+    streams = os.environ.get("SDEMC_MLMC_STREAMS", "1") != "0" and len(levels) >= 2
     with torch.cuda.device(dev):
+        if plan is None and streams and GRAPH_LEVELS:
+            ranges, counts = [], []
+            for n in trials:
+                lo = solver._take_paths(int(n))
+                off, cnt = E.shard(int(n), ctx.rank, ctx.size)
+                ranges.append((lo + off, cnt))
+                counts.append(cnt)
+            key = (dev, ctx.seed, ctx.rank, ctx.size, ctx.use64, bytes(ctx.sde0), bytes(ctx.po),
+                   bytes(ctx.coeffs64) if ctx.use64 else b"", tuple(int(l) for l in levels), tuple(counts))
+            g = _graphs.get(key)
+            if g is None:
+                if len(_graphs) >= 8:
+                    _graphs.pop(next(iter(_graphs)))
+                g = _graphs[key] = _GraphedPass(solver, payoff, discounter, counts, levels, ctx)
+            return g.run(ranges).all_reduce()
         out = LevelMoments(dev, len(levels))
         rows = [out.buf[i] for i in range(len(levels))]
         dr = [(plan, i) if plan is not None else None for i in range(len(levels))]
-        if os.environ.get("SDEMC_MLMC_STREAMS", "1") == "0" or len(levels) < 2:
+        if not streams:
             for n, f, c, row, d in zip(trials, levels, coarse, rows, dr):
                 _level_moments(solver, payoff, discounter, n, f, c, row, d, reduce=False, ctx=ctx)
             return out.all_reduce()

@@ -309,3 +309,36 @@ def test_packed_kernel_restated_iteration_matches_generic_iteration(steps, exact
     # difference (a different draw, mesh or hit) moves them by >= 1e-3 per path
     for key in ("sum", "sumsq", "sum_c", "sumsq_c", "sum_pc"):
         assert abs(a[key] - b[key]) <= 2e-6 * n, (key, a[key], b[key])
+
+
+def test_graph_replay_of_a_pass_equals_queued_launches():
+    """opt-in: mc_multilevel / get_optimal_trials replay a captured CUDA graph of the per-level launches (mlmc._GraphedPass):
+    same kernels, same global path ids => the (levels, 8) fp64 moments are those of the plain launches bit for bit,
+    call after call (every call advances the path ids, which the graph reads from device memory)."""
+    from sde_mc_b200 import mlmc as M
+    levels, trials = [1, 2, 4, 8, 16], [200_000, 50_000, 30_000, 20_000, 10_001]
+    call, csr = sm.EuroCall(1.0), sm.ConstantShortRate(0.02)
+    mk = lambda: sm.JumpEulerSolver(sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.]), 1), 3, 1, device=DEV,
+                                    seed=11, exact_jumps=True)
+    a, b = mk(), mk()
+    got, want = [], []
+    saved = M.GRAPH_LEVELS
+    M.GRAPH_LEVELS = True
+    try:
+        for _ in range(3):
+            got.append(M._all_levels(a, call, csr, trials, levels).read())
+        s1 = sm.mc_multilevel(trials, levels, mk(), call, csr)
+    finally:
+        M.GRAPH_LEVELS = saved
+    M.GRAPH_LEVELS = False
+    try:
+        for _ in range(3):
+            want.append(M._all_levels(b, call, csr, trials, levels).read())
+        s2 = sm.mc_multilevel(trials, levels, mk(), call, csr)
+    finally:
+        M.GRAPH_LEVELS = saved
+    assert got == want
+    assert got[0] != got[1]                      # different paths every call
+    assert a._next_path == b._next_path == 3 * sum(trials)
+    # and the public estimator on top of it
+    assert s1.sample_mean == s2.sample_mean and s1.sample_std == s2.sample_std
