@@ -191,7 +191,7 @@ typedef struct {
   double reserved;
 } sdemc_moments;
 
-#define SDEMC_OUT_NO_TMA 1u /* uniform-grid path-storing kernel: 16-byte LSU stores even where the layout allows TMA tiles */
+#define SDEMC_OUT_NO_TMA 1u /* path-storing kernels: 16-byte LSU stores even where the layout allows TMA tiles */
 
 /* Optional trajectory outputs, layouts exactly as the reference allocates them (solvers.py:64-66,150-162).
  * S = num_steps for the diffusion solver, num_steps + max_jumps for the jump solver.  NULL = skip.

@@ -7,7 +7,9 @@
 #include "jump1d.cuh"
 #include "debug_draws.cuh"
 #include "jump_flat.cuh"
+#include "jump_tma.cuh"
 #include "launch.cuh"
+#include "tma_host.cuh"
 
 namespace sdemc {
 namespace {
@@ -26,6 +28,70 @@ int run(const LaunchArgs& a) {
                                            a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
+}
+
+// path-storing launch through TMA (jump_tma.cuh); returns 1 when the layout does not qualify
+template <class C, int JSRC, bool FULL>
+int run_store_tma_inst(const LaunchArgs& a) {
+  const DevOut& o = a.out;
+  const uint64_t S = (uint64_t)o.S, rows = a.range.n_paths;
+  // the maps span the whole pitch (no box is cut inside a row)
+  const uint64_t len_s = tma_map_row_len((S + 1) * C::DIM, o.pitch_state);
+  const uint64_t len_t = FULL ? tma_map_row_len(S + 1, o.pitch_times) : 0;
+  const uint64_t len_n = FULL ? tma_map_row_len(S * C::DIM * C::M, o.pitch_normals) : 0;
+  // a short last tile (<= 16 elements) is written with direct stores, whole 32-byte sectors (jump_tma.cuh)
+  auto rows_of = [](uint64_t elems, uint64_t len, uint64_t pitch) {
+    JumpTmaRows r{(int)len, 0x7fffffff, 0};
+    const uint64_t tail = elems % kTmaTileElems;
+    if (tail > 0 && tail <= 16 && pitch % kTmaTileElems == 0 && pitch >= elems) {
+      r.dcol = (int)(elems - tail);
+      r.dend = (int)((elems + 7) / 8 * 8);
+    }
+    return r;
+  };
+#ifdef SDEMC_JUMP_TMA_NO_DIRECT   // A/B builds only: the last tile always goes through TMA
+  const JumpTmaRows rs{(int)len_s, 0x7fffffff, 0}, rt{(int)len_t, 0x7fffffff, 0}, rn{(int)len_n, 0x7fffffff, 0};
+#else
+  const JumpTmaRows rs = rows_of((S + 1) * C::DIM, len_s, o.pitch_state), rt = rows_of(S + 1, len_t, o.pitch_times),
+                    rn = rows_of(S * C::DIM * C::M, len_n, o.pitch_normals);
+#endif
+  CUtensorMap mp, ml, mj, mt, mn;
+  if (!make_row_map(&mp, o.paths, rows, len_s, o.pitch_state)) return 1;
+  if (FULL) {
+    if (!make_row_map(&ml, o.left, rows, len_s, o.pitch_state) || !make_row_map(&mj, o.jumps, rows, len_s, o.pitch_state) ||
+        !make_row_map(&mt, o.times, rows, len_t, o.pitch_times) || !make_row_map(&mn, o.normals, rows, len_n, o.pitch_normals))
+      return 1;
+  } else {
+    ml = mj = mt = mn = mp;
+  }
+  auto kernel = jump_store_tma_kernel<C, JSRC, FULL>;
+  const size_t smem = (JSRC == JSRC_QUEUE ? (size_t)a.qdepth * kJumpTmaBlock * sizeof(float2) : 0) + 1024 +
+                      (size_t)(kJumpTmaBlock / 32) * (FULL ? 5 : 1) * kTmaTileBytes + SDEMC_JUMP_TMA_PAD;
+  SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = 0;
+  int rc = pick_grid(kernel, smem, rows, &grid, kJumpTmaBlock);
+  if (rc != SDEMC_OK) return rc;
+  kernel<<<grid, kJumpTmaBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, a.qdepth, mp, ml, mj,
+                                                   mt, mn, rs, rt, rn);
+  SDEMC_CUDA_CHECK(cudaGetLastError());
+  return SDEMC_OK;
+}
+template <class C, int JSRC>
+int run_store(const LaunchArgs& a) {
+  const DevOut& o = a.out;
+  const bool full = o.left && o.jumps && o.times && o.normals;
+  const bool low = !o.left && !o.jumps && !o.times && !o.normals;
+  bool ok = !a.no_tma && a.range.n_paths < (1ull << 31) && !a.range.dyn && (full || low) &&
+            tma_rows_ok(o.paths, o.pitch_state);
+  if (ok && full)
+    ok = tma_rows_ok(o.left, o.pitch_state) && tma_rows_ok(o.jumps, o.pitch_state) && tma_rows_ok(o.times, o.pitch_times) &&
+         tma_rows_ok(o.normals, o.pitch_normals);
+  if (ok) {
+    const int rc = full ? run_store_tma_inst<C, JSRC, true>(a) : run_store_tma_inst<C, JSRC, false>(a);
+    if (rc <= 0) return rc;
+  }
+  // any other layout (dense rows, a subset of the arrays): the 16-byte-store kernel of store_tile.cuh
+  return run<C, JSRC, true>(a);
 }
 
 // moments-only fast path for 1-D single-driver models with queued (sparse) jumps: jump1d.cuh
@@ -98,7 +164,7 @@ int by_mode(const LaunchArgs& a) {
     if (!a.use_inject && !a.store && a.qdepth > 0 && !a.sde.milstein)
       return a.sde.exact_jumps ? run_1d<C, true>(a) : run_1d<C, false>(a);
   }
-  if (a.use_inject) return a.store ? run<C, JSRC_INJECT, true>(a) : SDEMC_ERR_UNSUPPORTED;
+  if (a.use_inject) return a.store ? run_store<C, JSRC_INJECT>(a) : SDEMC_ERR_UNSUPPORTED;
   if (a.short_path != SDEMC_SHORT_OFF && !a.store && a.qdepth == 0) {
     if (a.short_path == SDEMC_SHORT_ALIGNED) return run_flat<C>(a);
     // PACKED / PACKED_GENERIC: the stream of its own, 1-D lognormal-mark models only
@@ -110,8 +176,8 @@ int by_mode(const LaunchArgs& a) {
     }
     return SDEMC_ERR_UNSUPPORTED;
   }
-  if (a.qdepth > 0) return a.store ? run<C, JSRC_QUEUE, true>(a) : run<C, JSRC_QUEUE, false>(a);
-  return a.store ? run<C, JSRC_INLINE, true>(a) : run<C, JSRC_INLINE, false>(a);
+  if (a.qdepth > 0) return a.store ? run_store<C, JSRC_QUEUE>(a) : run<C, JSRC_QUEUE, false>(a);
+  return a.store ? run_store<C, JSRC_INLINE>(a) : run<C, JSRC_INLINE, false>(a);
 }
 
 template <int FAMILY, int M, int MARKS>

@@ -61,13 +61,26 @@ class SdeSolver(ABC):
         self.jump_strategy = L.JUMPS_AUTO    # sdemc_jump_strategy: how the kernels draw compound-Poisson jumps
         self.queue_depth = 0                 # QUEUE strategy: pre-drawn jumps per refill (0 = sized from rate * T)
         self.short_path = L.SHORT_AUTO       # sdemc_short_path: persistent-lane kernels for short paths
-        self.tma_store = True                # uniform-grid solve(): TMA tiles where the layout allows them
+        self.tma_store = True                # solve(): TMA tiles where the layout allows them
         # Row pitch of stored trajectories in floats: rows are padded to a multiple of this (32 floats = one
         # 128-byte line) so the path-storing kernels can use 16-byte vector stores.  Set to 1 for the reference's
         # dense (contiguous) allocations -- same values, 4-byte store path.
         self.row_align = 32
+        # A list here makes solve() append a (start, end) pair of CUDA events recorded around its kernel launch on the
+        # current stream (bench.py: the launch duration behind roofline.achieved, without allocation and host gaps).
+        self.kernel_events = None
 
     # ---- engine plumbing -----------------------------------------------------------------------------------
+    def _record_kernel_event(self, start):
+        """kernel_events hook: called before (start=None) and after the launch of solve()'s kernel."""
+        if self.kernel_events is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if start is not None:
+            self.kernel_events.append((start, ev))
+        return ev
+
     def _compute_device(self):
         dev = torch.device(self.device)
         if dev.type == 'cuda':
@@ -158,8 +171,10 @@ class DiffusionSolver(SdeSolver):
                 keep.append(z)
                 inj = L.SdemcInject(L.ptr(z), None, None, None, S)
             rng = L.SdemcRange(int(self.seed), self._take_paths(bs), bs)
+            ev = self._record_kernel_event(None)
             getattr(lib, 'check', L.check)(lib.sdemc_solve_paths(sde, want_payoff, rng, inj, out, L.ptr(L.workspace(dev)),
                                                                   L.stream_ptr(dev)))
+            self._record_kernel_event(ev)
         paths, normals = self._to_user_device(paths), self._to_user_device(normals)
         if want_payoff is not None:
             return paths, normals, self._to_user_device(payoffs)
@@ -257,10 +272,13 @@ class JumpDiffusionSolver(SdeSolver):
                 times, p_times = _alloc_rows(bs, (S + 1,), dev, self.row_align)
                 normals, p_norm = _alloc_rows(bs, (S, d) if m == 1 else (S, d, m), dev, self.row_align)
             out = L.SdemcPathsOut(L.ptr(paths), L.ptr(left), L.ptr(times), L.ptr(jumps), L.ptr(normals),
-                                  L.ptr(payoffs), L.ptr(iters), L.ptr(total), p_state, p_times, p_norm)
+                                  L.ptr(payoffs), L.ptr(iters), L.ptr(total), p_state, p_times, p_norm,
+                                  flags=0 if self.tma_store else L.OUT_NO_TMA)
             rng = L.SdemcRange(int(self.seed), self._take_paths(bs), bs)
+            ev = self._record_kernel_event(None)
             getattr(lib, 'check', L.check)(lib.sdemc_solve_paths(sde, want_payoff, rng, inj, out, L.ptr(L.workspace(dev)),
                                                                   L.stream_ptr(dev)))
+            self._record_kernel_event(ev)
             total_steps = int(total.item())
         self.last_iters = iters
         u = self._to_user_device

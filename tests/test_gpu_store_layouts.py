@@ -1,6 +1,6 @@
 """Path-storing mode: the three data paths out of the SM must write identical trajectories.
-  * TMA tiles (padded 128-byte row pitch, uniform-grid kernel)          csrc/diffusion_tma.cuh
-  * 16-byte vector flush (padded pitch, jump kernels / TMA disabled)    csrc/store_tile.cuh
+  * TMA tiles (padded 128-byte row pitch)                               csrc/diffusion_tma.cuh, csrc/jump_tma.cuh
+  * 16-byte vector flush (padded pitch, TMA disabled)                   csrc/store_tile.cuh
   * 4-byte scalar flush (dense rows = the reference's contiguous layout, row_align = 1)
 Checked bit for bit on the same seed, for ragged sizes (1 path, 33 paths, a non-multiple of the CTA size) and for
 shapes whose rows are not a multiple of the tile (partial tiles, clipped by the tensor map / scalar tail)."""
@@ -64,17 +64,81 @@ def test_heston_and_double_gbm_store_identical_across_layouts():
         assert torch.equal(a, b) and torch.equal(an, bn)
 
 
-@pytest.mark.parametrize("bs", [1, 33, 1000])
-def test_jump_store_identical_across_layouts(bs):
-    def factory():
-        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1)
-        return sm.JumpEulerSolver(sde, 3.0, 100, device=DEV, seed=3)
-
-    pa, (na, ta, la, ka, ja) = _solve(factory, bs, 32)
-    pb, (nb, tb, lb, kb, jb) = _solve(factory, bs, 1)
+def _assert_jump_outputs_equal(a, b):
+    pa, (na, ta, la, ka, ja) = a
+    pb, (nb, tb, lb, kb, jb) = b
     assert ka == kb
     for x, y in ((pa, pb), (na, nb), (ta, tb), (la, lb), (ja, jb)):
         assert x.shape == y.shape and torch.equal(x, y)
+
+
+@pytest.mark.parametrize("bs", [1, 33, 1000, 4097])
+@pytest.mark.parametrize("steps", [1, 7, 24, 100])
+def test_jump_store_identical_across_layouts(bs, steps):
+    """Merton 1-D (queued jumps): TMA tiles (jump_tma.cuh) == 16-byte vector flush == dense scalar flush, for row
+    lengths that are / are not whole super-groups of 12 iterations and whole tiles of 32 elements."""
+    def factory():
+        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1)
+        return sm.JumpEulerSolver(sde, 3.0, steps, device=DEV, seed=3)
+
+    a = _solve(factory, bs, 32)
+    b = _solve(factory, bs, 1)
+    c = _solve(factory, bs, 32, tma=False)
+    _assert_jump_outputs_equal(a, b)
+    _assert_jump_outputs_equal(c, b)
+    pa, (na, ta, la, ka, ja) = a
     # the trajectories end at T and the time grid is non-decreasing
     assert float(ta[:, ka, 0].min()) >= 3.0 - 1e-6
     assert bool((ta[:, 1:ka + 1, 0] >= ta[:, :ka, 0]).all())
+    assert float(pa[:, 0].min()) == 1.0 and float(la[:, 0].max()) == 1.0 and float(ja[:, 0].abs().max()) == 0.0
+
+
+def _jump_models():
+    def merton2d():
+        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.ones(2), 2, sm.get_corr_matrix([0.4]))
+        return sm.JumpEulerSolver(sde, 3.0, 40, device=DEV, seed=11)
+
+    def merton3d():
+        sde = sm.Merton(0.02, 0.2, 2, -0.05, 0.3, torch.ones(3), 3)
+        return sm.JumpEulerSolver(sde, 1.0, 30, device=DEV, seed=12)
+
+    def explevy2d():   # 'indep' noise: normals (bs, S, 2, 2), dense (inline) jumps
+        levy = sm.ExpExampleLevy(1, 1, 0.5, 2, 0.02, 0.3, 0.2, 0.05, dim=2)
+        return sm.JumpEulerSolver(sm.LevySde(levy, torch.tensor([1., 1.])), 1.0, 32, device=DEV, seed=13)
+
+    def asian_merton():
+        sde = sm.AsianWrapper(sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1))
+        return sm.JumpEulerSolver(sde, 3.0, 50, device=DEV, seed=14)
+
+    def merton_exact():
+        sde = sm.Merton(0.02, 0.2, 4, -0.05, 0.3, torch.tensor([1.0]), 1)
+        return sm.JumpEulerSolver(sde, 3.0, 20, device=DEV, seed=15, exact_jumps=True)
+
+    return dict(merton2d=merton2d, merton3d=merton3d, explevy2d=explevy2d, asian_merton=asian_merton,
+                merton_exact=merton_exact)
+
+
+@pytest.mark.parametrize("model", sorted(_jump_models()))
+def test_jump_store_multidim_identical_across_layouts(model):
+    factory = _jump_models()[model]
+    b = _solve(factory, 515, 1)
+    _assert_jump_outputs_equal(_solve(factory, 515, 32), b)
+    _assert_jump_outputs_equal(_solve(factory, 515, 32, tma=False), b)
+
+
+@pytest.mark.parametrize("bs", [33, 2000])
+def test_jump_low_storage_identical_across_layouts(bs):
+    """low_storage=True (solvers.py:152-153): only `paths` is produced; TMA kernel with one array."""
+    outs = []
+    for align, tma in ((32, True), (1, True), (32, False)):
+        sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1)
+        solver = sm.JumpEulerSolver(sde, 3.0, 100, device=DEV, seed=3)
+        solver.row_align, solver.tma_store = align, tma
+        paths, aux = solver.solve(bs=bs, low_storage=True)
+        assert aux[0] is None and aux[1] is None and aux[2] is None and aux[4] is None
+        outs.append((paths, aux[3]))
+    full = sm.JumpEulerSolver(sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1), 3.0, 100, device=DEV, seed=3)
+    ref = full.solve(bs=bs)[0]
+    for paths, k in outs:
+        assert k == outs[0][1] and torch.equal(paths, outs[0][0])
+    assert torch.equal(outs[0][0], ref)
