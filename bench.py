@@ -91,10 +91,10 @@ PROFILE = {
                       inst=667.7, binding=None, pipe_pct=dict(issue=43.7, fma=5.6, alu=44.8, xu=6.2, tensor=41.9)),
     "mlmc": dict(source="profiles/r02_ncu_mlmc.summary.txt", capture_paths=None, dram_bytes=15104.0, inst=None,
                  binding=None, pipe_pct=dict(issue=68.5, fma=26.2, alu=55.0, xu=44.0)),
-    "gbm_store": dict(source="profiles/r02_ncu_gbm_store.summary.txt", capture_paths=4e6, dram_bytes=8.25387e9,
-                      inst=None, binding=None, pipe_pct=dict(issue=37.6, fma=16.4, alu=25.9, xu=21.8)),
-    "merton_store": dict(source="profiles/r02_ncu_merton_store.summary.txt", capture_paths=2e6, dram_bytes=5.71235e9,
-                         inst=None, binding=None, pipe_pct=dict(issue=48.5, fma=15.2, alu=28.7, xu=9.4)),
+    "gbm_store": dict(source="profiles/r02_ncu_gbm_store.summary.txt", capture_paths=4e6, dram_bytes=8.13233e9,
+                      inst=None, binding=None, pipe_pct=dict(issue=53.3, fma=21.9, alu=40.5, xu=30.5)),
+    "merton_store": dict(source="profiles/r02_ncu_merton_store.summary.txt", capture_paths=2e6, dram_bytes=5.401e9,
+                         inst=None, binding=None, pipe_pct=dict(issue=36.3, fma=14.3, alu=20.5, xu=13.2)),
 }
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 

@@ -37,8 +37,8 @@
 
 #include <type_traits>
 
-#include "diffusion_tma.cuh"
 #include "jump.cuh"
+#include "tma_gang.cuh"
 
 namespace sdemc {
 
@@ -49,129 +49,6 @@ namespace sdemc {
 #define SDEMC_JUMP_TMA_PAD 0      // A/B builds only: unused shared memory per CTA (lowers the residency)
 #endif
 constexpr int kJumpTmaBlock = SDEMC_JUMP_TMA_BLOCK;
-static_assert(kTmaTileElems == 32, "jump_tma.cuh stages 128-byte rows");
-
-// Bulk-group bookkeeping of a warp.  Every lane carries the same values; only lane 0 talks to the engine.
-struct TmaGroups {
-  int committed;  // bulk groups committed so far
-  bool open;      // copies issued since the last commit
-  __device__ __forceinline__ void init() {
-    committed = 0;
-    open = false;
-  }
-  __device__ __forceinline__ void close() {
-    if (open) {
-      if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      ++committed;
-      open = false;
-    }
-  }
-  // returns once the engine has read the shared memory of every copy in groups 1 .. seq
-  __device__ __forceinline__ void acquire(int seq) {
-    close();
-    const int allowed = committed - seq;  // newer groups that may stay pending (wait_group takes an immediate)
-    if ((threadIdx.x & 31) == 0) {
-      if (allowed >= 3) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
-      else if (allowed == 2) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-      else if (allowed == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    __syncwarp();
-  }
-  // before the CTA retires: everything written
-  __device__ __forceinline__ void drain() {
-    close();
-    if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-};
-
-// what the host tells the kernel about the rows of one gang of arrays
-struct JumpTmaRows {
-  int len;   // columns the tensor maps declare (the pitch when rows are padded to whole tiles)
-  int dcol;  // first column written with direct stores instead of a tile (INT_MAX: none)
-  int dend;  // end of the directly written columns (the row's elements rounded up to whole 32-byte sectors)
-};
-
-// N output arrays of one warp that fill in lock-step: one single-buffered swizzled [32][32] tile each, consecutive
-// in shared memory, filled four elements per array at a time.
-template <int N>
-struct TmaGang {
-  static constexpr uint32_t kBytes = (uint32_t)N * kTmaTileBytes;  // shared memory per warp
-  uint32_t tiles;         // shared-window address of the first tile
-  uint32_t lane_addr[N];  // this lane's chunk 0 of its row in every tile, swizzle applied: + row * 128 + ((row & 7) << 4)
-  const CUtensorMap* map[N];
-  int row_len;            // columns the tensor maps declare
-  int dcol, dend;         // columns [dcol, dend) leave through direct 16-byte stores (short last tile; dcol = INT_MAX: none)
-  int seq;                // bulk group of the last copies out of the tiles (0: none pending)
-  int vec4;               // 16-byte vectors staged in the tiles, times 16 (warp-uniform)
-  int col;                // first column of the tiles
-  int row0;               // row of lane 0
-
-  __device__ __forceinline__ void init(uint32_t tiles_s, const JumpTmaRows& rows) {
-    const uint32_t q = threadIdx.x & 31;
-    tiles = tiles_s;
-#pragma unroll
-    for (int a = 0; a < N; ++a) lane_addr[a] = tiles_s + (uint32_t)a * kTmaTileBytes + q * 128u + ((q & 7u) << 4);
-    row_len = rows.len;
-    dcol = rows.dcol;
-    dend = rows.dend;
-    seq = 0;
-    vec4 = 0;
-    col = 0;
-    row0 = 0;
-  }
-  __device__ __forceinline__ void begin_rows(int first_row) {
-    col = 0;
-    row0 = first_row;
-  }
-  // before the stores of a vector: the first store into tiles the engine may still be reading waits for it
-  __device__ __forceinline__ void begin(TmaGroups& g) {
-    if (vec4 == 0 && seq != 0) {
-      g.acquire(seq);
-      seq = 0;
-    }
-  }
-  // four consecutive elements of this lane's path in array a
-  __device__ __forceinline__ void store(int a, float x0, float x1, float x2, float x3) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lane_addr[a] ^ (uint32_t)vec4), "f"(x0), "f"(x1),
-                 "f"(x2), "f"(x3)
-                 : "memory");
-  }
-  // The short last tile of a row (at most 16 elements: 134 = 4 x 32 + 6 slots for 100 nominal steps) does not go
-  // through a tile: a box costs the engine the same ~185 cycles whether 6 or 32 of its columns exist, and the kernel
-  // is bound by the engine's box rate.  Each lane writes its row's last one or two 32-byte sectors itself, whole
-  // sectors (the surplus lands in the row's padding).
-  __device__ __forceinline__ bool direct() const { return col >= dcol; }
-  __device__ __forceinline__ void store_direct(float* base, uint64_t pitch, bool row_ok, float x0, float x1, float x2,
-                                               float x3) {
-    const int c = col + (vec4 >> 2);
-    if (row_ok && c < dend)
-      *reinterpret_cast<float4*>(base + (uint64_t)(row0 + (int)(threadIdx.x & 31)) * pitch + c) = make_float4(x0, x1, x2, x3);
-  }
-  __device__ __forceinline__ void end_direct() { vec4 += 16; }
-  __device__ __forceinline__ void flush(TmaGroups& g) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my staging stores -> visible to the TMA engine
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0 && col < row_len) {
-#pragma unroll
-      for (int a = 0; a < N; ++a) tma_store_tile(map[a], tiles + (uint32_t)a * kTmaTileBytes, col, row0);
-    }
-    g.open = true;
-    seq = g.committed + 1;  // the group the next commit closes
-    vec4 = 0;
-    col += 32;
-  }
-  // after the stores of a vector
-  __device__ __forceinline__ void end(TmaGroups& g) {
-    vec4 += 16;
-    if (vec4 == 8 * 16) flush(g);
-  }
-  // end of the rows of this group of 32 paths
-  __device__ __forceinline__ void finish(TmaGroups& g) {
-    if (vec4 > 0 && !direct()) flush(g);
-    vec4 = 0;
-  }
-};
 
 enum { SG_FAST = 0, SG_GUARDED = 1, SG_IDLE = 2 };
 
@@ -182,8 +59,8 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
                           const DevInject inj, const DevOut out, const int qdepth,
                           const __grid_constant__ CUtensorMap map_paths, const __grid_constant__ CUtensorMap map_left,
                           const __grid_constant__ CUtensorMap map_jumps, const __grid_constant__ CUtensorMap map_times,
-                          const __grid_constant__ CUtensorMap map_normals, const JumpTmaRows rows_state,
-                          const JumpTmaRows rows_times, const JumpTmaRows rows_normals) {
+                          const __grid_constant__ CUtensorMap map_normals, const TmaRows rows_state,
+                          const TmaRows rows_times, const TmaRows rows_normals) {
   constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M, MARKS = C::MARKS;
   constexpr int NZ = BASE + (M == 2 ? 1 : 0);  // normals per iteration
   constexpr int SPB = steps_per_group(NZ);     // iterations served by one group of Philox blocks
@@ -214,19 +91,19 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
                               (threadIdx.x >> 5) * ((FULL ? 5u : 1u) * kTmaTileBytes);
   TmaGang<NSTATE> g_state;
   TmaGang<1> g_times, g_norm;
-  g_state.init(warp_tiles, rows_state);
-  g_state.map[0] = &map_paths;
+  g_state.init(warp_tiles, rows_state.dcol);
+  g_state.set_array(0, &map_paths, rows_state);
   if (FULL) {
-    g_state.map[1] = &map_left;
-    g_state.map[2] = &map_jumps;
-    if (TIMES_IN_STATE) {
-      g_state.map[3] = &map_times;
+    g_state.set_array(1, &map_left, rows_state);
+    g_state.set_array(2, &map_jumps, rows_state);
+    if (TIMES_IN_STATE) {  // (the host enables direct columns only when the time rows agree with the state rows)
+      g_state.set_array(3, &map_times, rows_times);
     } else {
-      g_times.init(warp_tiles + 3u * kTmaTileBytes, rows_times);
-      g_times.map[0] = &map_times;
+      g_times.init(warp_tiles + 3u * kTmaTileBytes, rows_times.dcol);
+      g_times.set_array(0, &map_times, rows_times);
     }
-    g_norm.init(warp_tiles + 4u * kTmaTileBytes, rows_normals);
-    g_norm.map[0] = &map_normals;
+    g_norm.init(warp_tiles + 4u * kTmaTileBytes, rows_normals.dcol);
+    g_norm.set_array(0, &map_normals, rows_normals);
   }
   TmaGroups grp;
   grp.init();
@@ -290,14 +167,15 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
     // vector v of the state rows / the time row / the increment row
     auto emit_state = [&](int v) {
       if (g_state.direct()) {
-        g_state.store_direct(out.paths, out.pitch_state, valid, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
+        g_state.begin(grp);
+        g_state.store_tail(0, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
         if (FULL) {
-          g_state.store_direct(out.left, out.pitch_state, valid, lb[4 * v], lb[4 * v + 1], lb[4 * v + 2], lb[4 * v + 3]);
-          g_state.store_direct(out.jumps, out.pitch_state, valid, jb[4 * v], jb[4 * v + 1], jb[4 * v + 2], jb[4 * v + 3]);
+          g_state.store_tail(1, lb[4 * v], lb[4 * v + 1], lb[4 * v + 2], lb[4 * v + 3]);
+          g_state.store_tail(2, jb[4 * v], jb[4 * v + 1], jb[4 * v + 2], jb[4 * v + 3]);
           if (TIMES_IN_STATE)
-            g_state.store_direct(out.times, out.pitch_times, valid, tb[4 * v], tb[4 * v + 1], tb[4 * v + 2], tb[4 * v + 3]);
+            g_state.store_tail(3, tb[4 * v], tb[4 * v + 1], tb[4 * v + 2], tb[4 * v + 3]);
         }
-        g_state.end_direct();
+        g_state.end_tail();
         return;
       }
       g_state.begin(grp);
@@ -311,8 +189,9 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
     };
     auto emit_times = [&](int v) {
       if (g_times.direct()) {
-        g_times.store_direct(out.times, out.pitch_times, valid, tb[4 * v], tb[4 * v + 1], tb[4 * v + 2], tb[4 * v + 3]);
-        g_times.end_direct();
+        g_times.begin(grp);
+        g_times.store_tail(0, tb[4 * v], tb[4 * v + 1], tb[4 * v + 2], tb[4 * v + 3]);
+        g_times.end_tail();
         return;
       }
       g_times.begin(grp);
@@ -321,8 +200,9 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
     };
     auto emit_norm = [&](int v) {
       if (g_norm.direct()) {
-        g_norm.store_direct(out.normals, out.pitch_normals, valid, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);
-        g_norm.end_direct();
+        g_norm.begin(grp);
+        g_norm.store_tail(0, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);
+        g_norm.end_tail();
         return;
       }
       g_norm.begin(grp);
@@ -440,9 +320,21 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
       for (int d = 1; d < 4; ++d) tb[d] = 0.0f;
       emit_times(0);
     }
+    if (g_state.direct()) {  // a short last tile: whole sectors written by the lanes themselves (tma_gang.cuh)
+      g_state.write_tail(0, out.paths, out.pitch_state, valid);
+      if (FULL) {
+        g_state.write_tail(1, out.left, out.pitch_state, valid);
+        g_state.write_tail(2, out.jumps, out.pitch_state, valid);
+        if (TIMES_IN_STATE) g_state.write_tail(3, out.times, out.pitch_times, valid);
+      }
+    }
     g_state.finish(grp);
     if (FULL) {
-      if (!TIMES_IN_STATE) g_times.finish(grp);
+      if (!TIMES_IN_STATE) {
+        if (g_times.direct()) g_times.write_tail(0, out.times, out.pitch_times, valid);
+        g_times.finish(grp);
+      }
+      if (g_norm.direct()) g_norm.write_tail(0, out.normals, out.pitch_normals, valid);
       g_norm.finish(grp);
     }
 

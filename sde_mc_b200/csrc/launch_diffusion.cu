@@ -25,13 +25,16 @@ int run_store_tma(const LaunchArgs& a) {
 #endif
   if (!make_row_map(&mp, a.out.paths, a.range.n_paths, len_p, a.out.pitch_state)) return 1;
   if (!make_row_map(&mn, a.out.normals, a.range.n_paths, len_n, a.out.pitch_normals)) return 1;
+  TmaRows rp = tma_rows_of((S + 1) * C::DIM, len_p, a.out.pitch_state), rn = tma_rows_of(S * NPS, len_n, a.out.pitch_normals);
+  if (C::DIM == NPS && C::DIM != 4) tma_rows_agree(rp, rn);  // one gang (diffusion_tma.cuh)
   auto kernel = diffusion_store_tma_kernel<C, HESTON, INJECT>;
-  const size_t smem = (size_t)(kTmaStoreBlock / 32) * 4 * kTmaTileBytes + 1024;
+  using Gang = TmaGang<2, kDiffTmaW>;
+  const size_t smem = (size_t)(kTmaStoreBlock / 32) * Gang::kBytes + Gang::kAlign;
   SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = 0;
   int rc = pick_grid(kernel, smem, a.range.n_paths, &grid, kTmaStoreBlock);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kTmaStoreBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, mp, mn);
+  kernel<<<grid, kTmaStoreBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, mp, mn, rp, rn);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
 }

@@ -39,22 +39,15 @@ int run_store_tma_inst(const LaunchArgs& a) {
   const uint64_t len_s = tma_map_row_len((S + 1) * C::DIM, o.pitch_state);
   const uint64_t len_t = FULL ? tma_map_row_len(S + 1, o.pitch_times) : 0;
   const uint64_t len_n = FULL ? tma_map_row_len(S * C::DIM * C::M, o.pitch_normals) : 0;
-  // a short last tile (<= 16 elements) is written with direct stores, whole 32-byte sectors (jump_tma.cuh)
-  auto rows_of = [](uint64_t elems, uint64_t len, uint64_t pitch) {
-    JumpTmaRows r{(int)len, 0x7fffffff, 0};
-    const uint64_t tail = elems % kTmaTileElems;
-    if (tail > 0 && tail <= 16 && pitch % kTmaTileElems == 0 && pitch >= elems) {
-      r.dcol = (int)(elems - tail);
-      r.dend = (int)((elems + 7) / 8 * 8);
-    }
-    return r;
-  };
 #ifdef SDEMC_JUMP_TMA_NO_DIRECT   // A/B builds only: the last tile always goes through TMA
-  const JumpTmaRows rs{(int)len_s, 0x7fffffff, 0}, rt{(int)len_t, 0x7fffffff, 0}, rn{(int)len_n, 0x7fffffff, 0};
+  const bool direct = false;
 #else
-  const JumpTmaRows rs = rows_of((S + 1) * C::DIM, len_s, o.pitch_state), rt = rows_of(S + 1, len_t, o.pitch_times),
-                    rn = rows_of(S * C::DIM * C::M, len_n, o.pitch_normals);
+  const bool direct = true;
 #endif
+  TmaRows rs = tma_rows_of((S + 1) * C::DIM, len_s, o.pitch_state, direct);
+  TmaRows rt = tma_rows_of(S + 1, len_t, o.pitch_times, direct && FULL);
+  const TmaRows rn = tma_rows_of(S * C::DIM * C::M, len_n, o.pitch_normals, direct && FULL);
+  if (FULL && C::DIM == 1) tma_rows_agree(rs, rt);  // the time rows ride in the state gang
   CUtensorMap mp, ml, mj, mt, mn;
   if (!make_row_map(&mp, o.paths, rows, len_s, o.pitch_state)) return 1;
   if (FULL) {

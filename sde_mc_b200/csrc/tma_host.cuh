@@ -2,7 +2,7 @@
 #pragma once
 #include <cudaTypedefs.h>
 
-#include "diffusion_tma.cuh"
+#include "tma_gang.cuh"
 
 namespace sdemc {
 namespace {
@@ -38,6 +38,25 @@ bool make_row_map(CUtensorMap* map, float* base, uint64_t n_rows, uint64_t row_l
 // allocation, sdemc_paths_out), else the row itself
 inline uint64_t tma_map_row_len(uint64_t row_len, uint64_t pitch) {
   return (pitch >= row_len && pitch % kTmaTileElems == 0) ? pitch : row_len;
+}
+
+// What a kernel needs to know about rows of `elems` elements: the declared length and, for a short last tile (at most
+// 16 elements), the columns it writes with direct stores, whole 32-byte sectors (tma_gang.cuh)
+inline TmaRows tma_rows_of(uint64_t elems, uint64_t len, uint64_t pitch, bool allow_direct = true) {
+  TmaRows r{(int)len, 0x7fffffff, 0};
+  const uint64_t tail = elems % kTmaTileElems;
+  if (allow_direct && tail > 0 && tail <= 16 && pitch % kTmaTileElems == 0 && pitch >= elems) {
+    r.dcol = (int)(elems - tail);
+    r.dend = (int)((elems + 7) / 8 * 8);
+  }
+  return r;
+}
+// arrays that share a gang switch to direct stores together or not at all
+inline void tma_rows_agree(TmaRows& a, TmaRows& b) {
+  if (a.dcol != b.dcol) {
+    a.dcol = b.dcol = 0x7fffffff;
+    a.dend = b.dend = 0;
+  }
 }
 
 inline bool tma_rows_ok(const float* base, uint64_t pitch) {

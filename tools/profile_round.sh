@@ -37,5 +37,5 @@ prof levy2d jump_kernel 5e6
 prof mlmc jump_flat1d_kernel 1
 prof merton_cv cv_kernel 2e6
 prof gbm_store diffusion_store_tma_kernel 4e6
-prof merton_store jump_kernel 2e6
+prof merton_store jump_store_tma_kernel 2e6
 ls -la $out | tail -30
