@@ -223,7 +223,10 @@ typedef struct {
  * driver of every component, integrate_cv varred.py:202-214) and dim for g (varred.py:124). */
 typedef struct {
   uint32_t struct_size; /* sizeof(sdemc_mlp) */
-  uint32_t reserved;
+  uint32_t cv_steps;    /* f only: the Brownian sum keeps the terms of the first cv_steps loop iterations -- the `tol`
+                           trimming of integrate_cv varred.py:202-209 with cv_steps = remove_steps(tol, steps, T)
+                           (helpers.py:71-74; steps = num_steps for diffusions, the batch's total_steps for the jump
+                           solver).  0 = keep all.  The jump and compensator sums are never trimmed (varred.py:124-127). */
   const float* d_w[4];
   const float* d_b[4];
   int32_t in_dim, hidden, out_dim, n_hidden_layers; /* n_hidden_layers == 3 */

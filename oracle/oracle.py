@@ -172,25 +172,30 @@ def mlp_struct(weights, biases):
     return m
 
 
-def cv_gamma_jump(sde, res, payoffs, disc_rate, jump_mean, f, g):
-    """per-path gamma from the arrays returned by jump(..., full=True)"""
+def remove_steps(tol, steps, time_interval):
+    """helpers.py:71-74: index of the last step kept when `tol` is cut off the end of the interval"""
+    return int(np.floor(steps - tol / (time_interval / steps)))
+
+
+def cv_gamma_jump(sde, res, payoffs, disc_rate, jump_mean, f, g, brownian_steps=0):
+    """per-path gamma from the arrays returned by jump(..., full=True); brownian_steps: integrate_cv's tol cut"""
     lib = load()
     n, K1, d = res["paths"].shape
     normals = res["normals"].reshape(n, K1 - 1, -1)
     gamma = np.empty((n,), np.float32)
     lib.oracle_cv_gamma_jump_f32(C.byref(sde), C.c_int64(n), C.c_int(K1 - 1), C.c_int(int(res["total_steps"])),
-                                 C.c_double(disc_rate), C.c_double(jump_mean), C.byref(f),
+                                 C.c_int(int(brownian_steps)), C.c_double(disc_rate), C.c_double(jump_mean), C.byref(f),
                                  C.byref(g) if g is not None else None, _p(res["paths"]), _p(res["left"]),
                                  _p(res["times"]), _p(res["jumps"]), _p(_c(normals, np.float32)),
                                  _p(_c(payoffs, np.float32)), _p(gamma))
     return gamma
 
 
-def cv_gamma_diffusion(sde, paths, normals, payoffs, disc_rate, f):
+def cv_gamma_diffusion(sde, paths, normals, payoffs, disc_rate, f, brownian_steps=0):
     lib = load()
     n = paths.shape[0]
     gamma = np.empty((n,), np.float32)
-    lib.oracle_cv_gamma_diffusion_f32(C.byref(sde), C.c_int64(n), C.c_double(disc_rate), C.byref(f),
+    lib.oracle_cv_gamma_diffusion_f32(C.byref(sde), C.c_int64(n), C.c_int(int(brownian_steps)), C.c_double(disc_rate), C.byref(f),
                                       _p(_c(paths, np.float32)), _p(_c(normals.reshape(n, paths.shape[1] - 1, -1), np.float32)),
                                       _p(_c(payoffs, np.float32)), _p(gamma))
     return gamma

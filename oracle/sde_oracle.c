@@ -120,8 +120,9 @@ static void mlp_forward(const oracle_mlp* net, const float* in, float* out) {
 }
 
 /* apply_adapted_control_variates varred.py:98-131 with the AdaptedPathData truncation nets.py:192-200
- * (the datasets drop the last time index) and integrate_cv varred.py:202-214 (tol = 0). */
-void oracle_cv_gamma_jump_f32(const oracle_sde* s, int64_t n, int K, int total_steps, double disc_rate,
+ * (the datasets drop the last time index) and integrate_cv varred.py:202-214: the Brownian sum keeps the first
+ * brownian_steps = remove_steps(tol, total_steps, T) steps (helpers.py:71-74; <= 0: all, tol = 0). */
+void oracle_cv_gamma_jump_f32(const oracle_sde* s, int64_t n, int K, int total_steps, int brownian_steps, double disc_rate,
                               double jump_mean, const oracle_mlp* f, const oracle_mlp* g, const float* paths,
                               const float* left, const float* times, const float* jumps, const float* normals,
                               const float* payoffs, float* gamma) {
@@ -139,7 +140,7 @@ void oracle_cv_gamma_jump_f32(const oracle_sde* s, int64_t n, int K, int total_s
       mlp_forward(f, in, fo);
       float acc = 0.f;
       for (int i = 0; i < d * m; ++i) acc += normals[(p * K + k) * d * m + i] * fo[i];
-      bcv += (double)(acc * D);
+      if (brownian_steps <= 0 || k < brownian_steps) bcv += (double)(acc * D);          /* varred.py:203-209 */
       if (g) {
         for (int i = 0; i < d; ++i) in[1 + i] = left[(p * (K + 1) + k) * d + i];
         mlp_forward(g, in, go);
@@ -154,8 +155,9 @@ void oracle_cv_gamma_jump_f32(const oracle_sde* s, int64_t n, int K, int total_s
   }
 }
 
-/* apply_diffusion_control_variate varred.py:75-95: time points partition(T, steps, 'left') helpers.py:6-33 */
-void oracle_cv_gamma_diffusion_f32(const oracle_sde* s, int64_t n, double disc_rate, const oracle_mlp* f,
+/* apply_diffusion_control_variate varred.py:75-95: time points partition(T, steps, 'left') helpers.py:6-33; the sum
+ * keeps the first brownian_steps = remove_steps(tol, num_steps, T) steps (<= 0: all) */
+void oracle_cv_gamma_diffusion_f32(const oracle_sde* s, int64_t n, int brownian_steps, double disc_rate, const oracle_mlp* f,
                                    const float* paths, const float* normals, const float* payoffs, float* gamma) {
   const int d = s->dim, m = s->m, S = s->num_steps;
   const float r = (float)disc_rate;
@@ -170,7 +172,7 @@ void oracle_cv_gamma_diffusion_f32(const oracle_sde* s, int64_t n, double disc_r
       mlp_forward(f, in, fo);
       float acc = 0.f;
       for (int i = 0; i < d * m; ++i) acc += normals[(p * S + k) * d * m + i] * fo[i];
-      bcv += (double)(acc * D);
+      if (brownian_steps <= 0 || k < brownian_steps) bcv += (double)(acc * D);
     }
     gamma[p] = (float)((double)payoffs[p] + bcv);
   }

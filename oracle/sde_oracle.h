@@ -86,11 +86,11 @@ void oracle_icdf_f32(const double* mark_p, int64_t n, const float* u, float* out
 /* apply_adapted_control_variates varred.py:98-131 / apply_diffusion_control_variate varred.py:75-95, per path.
  * Consumes the arrays of oracle_jump_f32 (K slots) / oracle_diffusion_f32; total_steps = number of valid
  * iterations (global).  g may be NULL.  gamma (n) = payoff + brownian cv + jump cv + compensator. */
-void oracle_cv_gamma_jump_f32(const oracle_sde* s, int64_t n, int K, int total_steps, double disc_rate,
+void oracle_cv_gamma_jump_f32(const oracle_sde* s, int64_t n, int K, int total_steps, int brownian_steps, double disc_rate,
                               double jump_mean, const oracle_mlp* f, const oracle_mlp* g, const float* paths,
                               const float* left, const float* times, const float* jumps, const float* normals,
                               const float* payoffs, float* gamma);
-void oracle_cv_gamma_diffusion_f32(const oracle_sde* s, int64_t n, double disc_rate, const oracle_mlp* f,
+void oracle_cv_gamma_diffusion_f32(const oracle_sde* s, int64_t n, int brownian_steps, double disc_rate, const oracle_mlp* f,
                                    const float* paths, const float* normals, const float* payoffs, float* gamma);
 
 /* Philox4x32-10 replay of the kernels' in-register noise (same counter layout, libm transcendentals instead

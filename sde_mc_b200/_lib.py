@@ -90,7 +90,7 @@ class SdemcPathsOut(_Sized):
 
 
 class SdemcMlp(_Sized):
-    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("d_w", C.c_void_p * 4),
+    _fields_ = [("struct_size", C.c_uint32), ("cv_steps", C.c_uint32), ("d_w", C.c_void_p * 4),
                 ("d_b", C.c_void_p * 4), ("in_dim", C.c_int32), ("hidden", C.c_int32), ("out_dim", C.c_int32),
                 ("n_hidden_layers", C.c_int32)]
 

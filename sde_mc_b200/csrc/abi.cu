@@ -311,6 +311,7 @@ int sdemc_mc_cv(const sdemc_sde* sde, const sdemc_payoff* payoff, float disc_rat
   cv.disc_rate_l2e = (float)((double)disc_rate * 1.4426950408889634);
   cv.comp_c = (float)(-(double)sde->rate * (double)jump_mean);
   cv.last_interval = (inject && inject->total_steps > 0) ? inject->total_steps - 1 : 0x7fffffff;
+  cv.brownian_steps = f->cv_steps > 0 ? (int)f->cv_steps : 0x7fffffff;
   cv.gamma_out = d_gamma_out;
   return launch_cv(*sde, a, mlp_dev(f), mlp_dev(g), cv);
 }

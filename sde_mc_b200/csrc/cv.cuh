@@ -257,6 +257,7 @@ struct DevCv {
   float disc_rate_l2e;  // r * log2(e):  D(t) = 2^(-t r log2 e)   (ConstantShortRate options.py:334-337)
   float comp_c;         // - rate * E[J]                            (varred.py:126)
   int last_interval;    // compensator intervals with index >= last_interval are dropped (varred.py:104,126-127)
+  int brownian_steps;   // f dW terms of iterations >= brownian_steps are dropped (integrate_cv tol, varred.py:203-209)
   float* gamma_out;     // (n) per-path gamma or nullptr
 };
 
@@ -525,10 +526,11 @@ __global__ void __launch_bounds__(kCvThreads, 2) cv_kernel(const DevSde s, const
         }
         correlate<C>(s, z1, w1);
         euler_step<C>(s, xv, dt, sq, w1, w2);
+        const float Df = k < cv.brownian_steps ? D : 0.0f;           // tol > 0: the last steps carry no f dW term
 #pragma unroll
         for (int d = 0; d < BASE; ++d) {
-          cf[d * M] = D * (w1[d] * sq);                              // f_{d,0} dW_{d,0}
-          if (M == 2) cf[d * M + 1] = D * (zn[BASE] * sq);           // f_{d,1} dW_{.,1}: the common driver
+          cf[d * M] = Df * (w1[d] * sq);                             // f_{d,0} dW_{d,0}
+          if (M == 2) cf[d * M + 1] = Df * (zn[BASE] * sq);          // f_{d,1} dW_{.,1}: the common driver
         }
         if constexpr (JUMPS) {
           cg = D * (k < cv.last_interval ? fmaf(cv.comp_c, dt, p.Jprev) : p.Jprev);  // g J - rate E[J] g dt

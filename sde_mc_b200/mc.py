@@ -157,7 +157,7 @@ def mc_apply_cvs(models, solver, trials, payoff, discounter, sim_bs=1e5, bs=1000
     trials = int(trials)
     if (fused_cv_supported(models, solver, tol) and isinstance(discounter, ConstantShortRate)
             and _spec.payoff_kernel_spec(payoff) is not None):
-        mom = mc_cv_fused(models, solver, trials, payoff, discounter).read()
+        mom = mc_cv_fused(models, solver, trials, payoff, discounter, tol=tol).read()
         mean, stderr = E.mean_and_stderr(mom['sum'], mom['sumsq'], trials)
         return MCStatistics(mean, stderr, time.time() - start, trials)
     run_sum, run_sum_sq = 0, 0

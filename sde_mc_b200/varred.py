@@ -184,10 +184,12 @@ def fused_cv_supported(models, solver, tol=0):
     """True when `sdemc_mc_cv` can evaluate these nets: BN-free Linear/ReLU stacks with three equal hidden layers of
     width <= 63 (the architecture of the experiments) on a model shape the kernel is built for -- 1-D geometric
     'diag' SDEs (Gbm, Merton: merton_cv_experiment.py:37-38, Mlp(2, .., 1)) and the 2-D geometric 'indep' Levy SDE
-    (levy_rainbow_cv_experiment.py:39-40, f = Mlp(3, .., 4), g = Mlp(3, .., 2)) -- with a constant short rate and
-    tol == 0 (the trimming of varred.py:203-209 cuts at an index of the BATCH's longest path; a fused kernel has no
-    batch, so tol > 0 keeps the stored-trajectory route)."""
-    if tol != 0:
+    (levy_rainbow_cv_experiment.py:39-40, f = Mlp(3, .., 4), g = Mlp(3, .., 2)) -- with a constant short rate.
+    tol > 0 (integrate_cv varred.py:202-209) is fused for diffusions, where the cut index depends on num_steps only;
+    for the jump solver the reference cuts at an index derived from the BATCH's total_steps (the stored arrays are
+    trimmed to it, mc.py:394-396): a fused kernel has no batch, so that case keeps the stored-trajectory route
+    (the kernel itself takes the cut index: `mc_cv_fused(..., inject=dict(total_steps=...), tol=...)`)."""
+    if tol != 0 and solver.has_jumps:
         return False
     try:
         spec = _spec.spec_of(solver.sde)
@@ -208,9 +210,11 @@ def fused_cv_supported(models, solver, tol=0):
     return all(_export_mlp(n, 'cpu', keep, spec.dim + 1, o) is not None for n, o in zip(nets, outs))
 
 
-def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_out=False, dev_range=None):
+def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_out=False, dev_range=None, tol=0):
     """One launch: jump-adapted (or uniform) Euler + f/g MLPs on tensor cores + gamma + moments (sdemc_mc_cv).
-    dev_range: an _engine.DeviceRange -- the kernel reads its path range from device memory (run_cv_mc)."""
+    dev_range: an _engine.DeviceRange -- the kernel reads its path range from device memory (run_cv_mc).
+    tol: the Brownian control-variate sum keeps the first remove_steps(tol, steps, T) steps (varred.py:202-209);
+    steps = num_steps for diffusions, inject['total_steps'] for the jump solver (parity mode only)."""
     trials = int(trials)
     dev = solver._compute_device()
     lib = L.load()
@@ -220,6 +224,14 @@ def mc_cv_fused(models, solver, trials, payoff, discounter, inject=None, gamma_o
         d, m = solver.sde.dim, solver.sde.brown_dim // solver.sde.dim
         f = _export_mlp(nets[0], dev, keep, d + 1, d * m)
         g = _export_mlp(nets[1], dev, keep, d + 1, d) if solver.has_jumps else None
+        if tol != 0:
+            if solver.has_jumps and not (inject and inject.get('total_steps')):
+                raise L.SdemcError("tol > 0 with the jump solver needs the batch's total_steps (inject=dict(total_steps=..))")
+            steps = int(inject['total_steps']) if solver.has_jumps else int(solver.num_steps)
+            kept = remove_steps(tol, steps, solver.time_interval)
+            if kept <= 0:
+                raise L.SdemcError("tol = %r removes every step of the Brownian control variate" % (tol,))
+            f.cv_steps = kept
         rank, size = E.world()
         if dev_range is not None:
             lo, off, cnt = 0, 0, trials

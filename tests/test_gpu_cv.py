@@ -227,3 +227,49 @@ def test_fused_cv_other_widths_vs_torch_application(hidden):
     tol = 1.5e-2 * cv_scale + 1e-3
     assert err < tol
     assert abs(mom.read()["sum"] - float(ref.astype(np.float64).sum())) < tol * bs
+
+
+def test_fused_cv_tol_vs_reference_golden():
+    """tol > 0 (integrate_cv varred.py:202-209): the fused kernel drops the f dW terms from index
+    remove_steps(tol, steps, T) on (sdemc_mlp.cv_steps); jump and compensator sums are untouched.  Golden: the
+    unmodified reference with tol > 0 (tests/golden/make_golden_cv_tol.py)."""
+    gt = golden("cv_tol")
+    g = golden("cv_gbm_1d")
+    solver = sm.EulerSolver(sm.Gbm(0.02, 0.3, t(g["x0"]), 1), 3.0, 16, device=DEV)
+    f = _net_from_golden(g, "f")
+    n = g["z"].shape[0]
+    for tol in (0.5, 1.0):
+        assert sm.fused_cv_supported(f, solver, tol)
+        _, gam = sm.mc_cv_fused(f, solver, n, sm.EuroCall(1.0), sm.ConstantShortRate(0.02), inject=dict(z=g["z"]),
+                                gamma_out=True, tol=tol)
+        err = np.max(np.abs(gam.cpu().numpy() - gt["gbm_tol%g" % tol]))
+        assert err < CV_ATOL, (tol, err)
+    g = golden("cv_merton_1d")
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, t(g["x0"]), 1)
+    solver = sm.JumpEulerSolver(sde, 3.0, int(g["z"].shape[1]) - int(g["max_jumps"]), device=DEV)
+    f, gnet = _net_from_golden(g, "f"), _net_from_golden(g, "g")
+    assert not sm.fused_cv_supported([f, gnet], solver, 0.5)     # production: the cut index needs the batch
+    _, gam = sm.mc_cv_fused([f, gnet], solver, g["z"].shape[0], sm.EuroCall(1.0), sm.ConstantShortRate(0.02),
+                            inject=dict(z=g["z"], jump_times=g["jump_times"], marks=g["marks"],
+                                        total_steps=int(g["total_steps"])), gamma_out=True, tol=0.5)
+    err = np.max(np.abs(gam.cpu().numpy() - gt["merton_tol0.5"]))
+    assert err < CV_ATOL, err
+
+
+def test_mc_apply_cvs_with_tol_fused_equals_stored_route():
+    """mc_apply_cvs(..., tol) on a diffusion: the fused kernel against the reference-style application (PyTorch on
+    trajectories stored by the path-storing kernel) -- same estimate within the error bars, same variance."""
+    from sde_mc_b200 import varred
+    g = golden("cv_gbm_1d")
+    f = _net_from_golden(g, "f")
+    call, csr = sm.EuroCall(1.0), sm.ConstantShortRate(0.02)
+    mk = lambda seed: sm.EulerSolver(sm.Gbm(0.02, 0.3, torch.tensor([1.]), 1), 3.0, 16, device=DEV, seed=seed)
+    n = 400_000
+    fused = sm.mc_apply_cvs(f, mk(1), n, call, csr, sim_bs=10 ** 5, bs=2000, tol=0.5)
+    varred.FUSED_CV_ENABLED = False
+    try:
+        stored = sm.mc_apply_cvs(f, mk(7), n, call, csr, sim_bs=10 ** 5, bs=2000, tol=0.5)
+    finally:
+        varred.FUSED_CV_ENABLED = True
+    assert abs(float(fused.sample_mean) - float(stored.sample_mean)) <= 3 * math.hypot(float(fused.sample_std), float(stored.sample_std))
+    assert abs(float(fused.sample_std) ** 2 / float(stored.sample_std) ** 2 - 1.0) < 0.10

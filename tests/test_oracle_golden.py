@@ -165,3 +165,32 @@ def test_philox_known_answer():
         [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert oracle.philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_cv_gamma_with_tol_matches_reference():
+    """integrate_cv's `tol` (varred.py:202-209, remove_steps helpers.py:71-74): only the Brownian sum is cut, at an
+    index of num_steps (diffusion) resp. of the batch's total_steps (jump solver).  Golden: the unmodified reference
+    with tol > 0 on the nets and noise of cv_gbm_1d / cv_merton_1d (tests/golden/make_golden_cv_tol.py)."""
+    gt = golden("cv_tol")
+    g = golden("cv_gbm_1d")
+    solver = sm.EulerSolver(sm.Gbm(0.02, 0.3, t(g["x0"]), 1), 3.0, 16)
+    osde = oracle_sde(solver)
+    paths, normals = oracle.diffusion(osde, g["z"])
+    pay = oracle.payoff(oracle.payoff_struct(0, 1.0), paths[:, -1]) * np.float32(np.exp(-0.02 * 3.0))
+    for tol in (0.5, 1.0):
+        keep = oracle.remove_steps(tol, 16, 3.0)
+        assert keep == int(gt["gbm_keep%g" % tol])
+        gam = oracle.cv_gamma_diffusion(osde, paths, normals, pay, 0.02, _mlps(g, "f"), keep)
+        assert np.max(np.abs(gam - gt["gbm_tol%g" % tol])) < 2e-5
+        assert np.max(np.abs(gam - g["cv_gamma"])) > 1e-2          # the cut matters on this fixture
+    g = golden("cv_merton_1d")
+    sde = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, t(g["x0"]), 1)
+    solver = sm.JumpEulerSolver(sde, 3.0, int(g["z"].shape[1]) - int(g["max_jumps"]))
+    osde = oracle_sde(solver)
+    res = oracle.jump(osde, g["z"], None, g["jump_times"], g["marks"])
+    last = res["paths"][np.arange(len(res["iters"])), res["iters"]]
+    pay = oracle.payoff(oracle.payoff_struct(0, 1.0), last) * np.float32(np.exp(-0.02 * 3.0))
+    keep = oracle.remove_steps(0.5, int(res["total_steps"]), 3.0)
+    assert keep == int(gt["merton_keep0.5"])
+    gam = oracle.cv_gamma_jump(osde, res, pay, 0.02, float(g["jump_mean"]), _mlps(g, "f"), _mlps(g, "g"), keep)
+    assert np.max(np.abs(gam - gt["merton_tol0.5"])) < 2e-5
