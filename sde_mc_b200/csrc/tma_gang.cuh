@@ -133,7 +133,7 @@ struct TmaGang {
   uint32_t lane_addr[N];  // this lane's chunk 0 of its row in every tile, swizzle applied: + row * 128 + ((row & 7) << 4)
   const CUtensorMap* map[N];
   int row_len[N];         // columns the tensor map of every array declares
-  int dcol;               // from this column on the rows leave through direct 16-byte stores (short last tile;
+  int dcol;               // from this column on the rows leave through 32-byte sector stores (short last tile;
                           // INT_MAX: none) -- a property of the gang, the host only enables it when all arrays agree
   int dend[N];            // end of the directly written columns of every array
   int seq;                // bulk group of the last copies out of the tiles (0: none pending)
