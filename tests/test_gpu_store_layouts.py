@@ -4,6 +4,7 @@
   * 4-byte scalar flush (dense rows = the reference's contiguous layout, row_align = 1)
 Checked bit for bit on the same seed, for ragged sizes (1 path, 33 paths, a non-multiple of the CTA size) and for
 shapes whose rows are not a multiple of the tile (partial tiles, clipped by the tensor map / scalar tail)."""
+import math
 import os
 
 import numpy as np
@@ -142,3 +143,63 @@ def test_jump_low_storage_identical_across_layouts(bs):
     for paths, k in outs:
         assert k == outs[0][1] and torch.equal(paths, outs[0][0])
     assert torch.equal(outs[0][0], ref)
+
+
+def test_merton_full_storage_at_bench_size_is_self_consistent():
+    """The path-storing bench workload (Merton 1-D, 2e6 paths x 100 nominal steps, five arrays through TMA): every
+    stored slot is re-derived from its neighbours -- the size-independent form of the step-by-step parity tests.
+      times non-decreasing, 0 at index 0, T from the path's last iteration on        solvers.py:190-203
+      dt = times[k+1] - times[k] <= h0 and the increments are N(0, dt)                :194-197
+      left[k+1] = x[k] (1 + a dt + sigma dW[k])                                       schemes.py:5-9, :203
+      paths[k+1] = left[k+1] + x[k] J[k+1]   (exact_jumps = False: the jump acts on the pre-step state)  :214-222
+    and the idle tail repeats the final state (dt = 0)."""
+    mu, sigma, rate, alpha, gamma_, T, steps, n = 0.02, 0.2, 1.0, -0.05, 0.3, 3.0, 100, 2_000_000
+    sde = sm.Merton(mu, sigma, rate, alpha, gamma_, torch.tensor([1.0]), 1)
+    solver = sm.JumpEulerSolver(sde, T, steps, device=DEV, seed=21)
+    paths, (normals, times, left, total, jumps) = solver.solve(bs=n)
+    S = normals.shape[1]
+    assert paths.shape == (n, total + 1, 1) and times.shape == (n, S + 1, 1) and left.shape == jumps.shape == (n, S + 1, 1)
+    x, t, l, j, dw = paths[:, :, 0], times[:, :total + 1, 0], left[:, :total + 1, 0], jumps[:, :total + 1, 0], normals[:, :total, 0]
+    assert float(x[:, 0].min()) == 1.0 == float(x[:, 0].max()) and float(t[:, 0].abs().max()) == 0.0
+    dt = t[:, 1:] - t[:, :-1]
+    assert float(dt.min()) >= 0.0 and float(dt.max()) <= T / steps + 1e-6       # (differences of fp32 times)
+    assert float((t[:, -1] - T).abs().max()) <= 1e-6
+    a = mu - rate * (math.exp(alpha + 0.5 * gamma_ ** 2) - 1.0)        # compensated drift of the Merton model
+    pred_left = x[:, :-1] * (1.0 + a * dt + sigma * dw)
+    assert float(((l[:, 1:] - pred_left).abs() / l[:, 1:].abs().clamp_min(1e-3)).max()) < 2e-6
+    pred_x = l[:, 1:] + x[:, :-1] * j[:, 1:]
+    assert float(((x[:, 1:] - pred_x).abs() / x[:, 1:].abs().clamp_min(1e-3)).max()) < 2e-6
+    # increments: N(0, dt) -- standardised over the active steps
+    act = dt > 0
+    z = (dw[act] / dt[act].sqrt()).double()
+    assert abs(float(z.mean())) < 5.0 / math.sqrt(z.numel()) and abs(float(z.var()) - 1.0) < 5.0 * math.sqrt(2.0 / z.numel()) + 2e-6
+    # jumps: rate * T per path on average, marks lognormal - 1
+    nj = (j[:, 1:] != 0).sum(dim=1).double()
+    assert abs(float(nj.mean()) - rate * T) < 5.0 * math.sqrt(rate * T / n)
+    # idle tail: state and time repeat, no increments, no jumps
+    it = solver.last_iters.long()
+    k = torch.arange(total + 1, device=x.device)[None, :]
+    idle = k > it[:, None]
+    x_last = x.gather(1, it[:, None])
+    assert bool((x[idle] == x_last.expand_as(x)[idle]).all()) and bool(((t[idle] - T).abs() <= 1e-6).all()) and bool((j[idle] == 0).all())
+    assert bool((dw[idle[:, 1:]] == 0).all())
+    assert int(it.max()) == total
+
+
+def test_gbm_solve_at_bench_size_is_self_consistent():
+    """GBM solve() at the bench size (4e6 x 252, TMA gang of paths + increments): x[k+1] = x[k] (1 + mu h + sigma dW[k])
+    for every stored slot (schemes.py:5-9), increments N(0, h)."""
+    mu, sigma, T, steps, n = 0.02, 0.3, 3.0, 252, 4_000_000
+    solver = sm.EulerSolver(sm.Gbm(mu, sigma, torch.tensor([1.0]), 1), T, steps, device=DEV, seed=22)
+    paths, normals = solver.solve(bs=n)
+    x, dw = paths[:, :, 0], normals[:, :, 0]
+    h = T / steps
+    assert float(x[:, 0].min()) == 1.0 == float(x[:, 0].max())
+    worst = 0.0
+    for lo in range(0, n, 1_000_000):       # in slices: the check itself needs a few temporaries of the slice's size
+        xs, ds = x[lo:lo + 1_000_000], dw[lo:lo + 1_000_000]
+        pred = xs[:, :-1] * (1.0 + mu * h + sigma * ds)
+        worst = max(worst, float(((xs[:, 1:] - pred).abs() / xs[:, 1:].abs().clamp_min(1e-3)).max()))
+    assert worst < 2e-6, worst
+    z = (dw[:1_000_000] / math.sqrt(h)).double()
+    assert abs(float(z.mean())) < 5.0 / math.sqrt(z.numel()) and abs(float(z.var()) - 1.0) < 5.0 * math.sqrt(2.0 / z.numel()) + 2e-6
