@@ -80,21 +80,21 @@ OPS_PER_PATH_STEP.update({"gbm_store": 23.0, "merton_store": 40.0, "mlmc": 40.0}
 PROFILE = {
     "gbm": dict(source="profiles/r02_ncu_gbm.summary.txt", capture_paths=1e8, dram_bytes=20224.0, inst=14.59,
                 binding=dict(pipe="xu", inst=2.02, lanes_per_sm=16),
-                pipe_pct=dict(issue=65.6, fma=32.0, alu=45.0, xu=72.3)),
-    "merton": dict(source="profiles/r02_ncu_merton.summary.txt", capture_paths=5e7, dram_bytes=45568.0, inst=37.36,
+                pipe_pct=dict(issue=65.5, fma=32.0, alu=44.9, xu=72.3)),
+    "merton": dict(source="profiles/r02_ncu_merton.summary.txt", capture_paths=5e7, dram_bytes=45056.0, inst=37.36,
                    binding=dict(pipe="issue", inst=37.36, lanes_per_sm=128),
-                   pipe_pct=dict(issue=69.0, fma=34.0, alu=39.9, xu=45.6)),
+                   pipe_pct=dict(issue=69.1, fma=34.0, alu=39.9, xu=45.7)),
     "levy2d": dict(source="profiles/r02_ncu_levy2d.summary.txt", capture_paths=5e6, dram_bytes=36608.0, inst=145.3,
                    binding=dict(pipe="issue", inst=145.3, lanes_per_sm=128),
                    pipe_pct=dict(issue=65.6, fma=31.7, alu=45.9, xu=46.2)),
-    "merton_cv": dict(source="profiles/r02_ncu_merton_cv.summary.txt", capture_paths=2e6, dram_bytes=139520.0,
-                      inst=667.7, binding=None, pipe_pct=dict(issue=43.7, fma=5.6, alu=44.8, xu=6.2, tensor=41.9)),
-    "mlmc": dict(source="profiles/r02_ncu_mlmc.summary.txt", capture_paths=None, dram_bytes=15104.0, inst=None,
-                 binding=None, pipe_pct=dict(issue=68.5, fma=26.2, alu=55.0, xu=44.0)),
-    "gbm_store": dict(source="profiles/r02_ncu_gbm_store.summary.txt", capture_paths=4e6, dram_bytes=8.13233e9,
-                      inst=None, binding=None, pipe_pct=dict(issue=53.3, fma=21.9, alu=40.5, xu=30.5)),
-    "merton_store": dict(source="profiles/r02_ncu_merton_store.summary.txt", capture_paths=2e6, dram_bytes=5.401e9,
-                         inst=None, binding=None, pipe_pct=dict(issue=36.3, fma=14.3, alu=20.5, xu=13.2)),
+    "merton_cv": dict(source="profiles/r02_ncu_merton_cv.summary.txt", capture_paths=2e6, dram_bytes=189440.0,
+                      inst=667.7, binding=None, pipe_pct=dict(issue=43.6, fma=5.6, alu=44.9, xu=6.2, tensor=41.7)),
+    "mlmc": dict(source="profiles/r02_ncu_mlmc.summary.txt", capture_paths=None, dram_bytes=15616.0, inst=None,
+                 binding=None, pipe_pct=dict(issue=67.6, fma=25.8, alu=54.4, xu=43.5)),
+    "gbm_store": dict(source="profiles/r02_ncu_gbm_store.summary.txt", capture_paths=4e6, dram_bytes=8.13176e9,
+                      inst=None, binding=None, pipe_pct=dict(issue=53.2, fma=21.9, alu=40.5, xu=30.5)),
+    "merton_store": dict(source="profiles/r02_ncu_merton_store.summary.txt", capture_paths=2e6, dram_bytes=5.40102e9,
+                         inst=None, binding=None, pipe_pct=dict(issue=36.4, fma=14.2, alu=20.5, xu=13.2)),
 }
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 

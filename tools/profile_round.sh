@@ -18,10 +18,12 @@ except Exception as e:
 PY
 done
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_${tag}_reference.json 2>/dev/null
+timeout 300 python bench.py --gpus 1 --workload mlmc --scaling strong --no-cpu-baseline --steps 20 > $out/bench_${tag}_mlmc_strong_n1.json 2>/dev/null
 # launch list of the default bench command = the Merton north-star workload (cold-cache, serialised: shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_merton.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_merton.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_gbm.csv python bench.py --workload gbm --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_gbm.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_merton_store.csv python bench.py --workload merton_store --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_merton_store.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_gbm_store.csv python bench.py --workload gbm_store --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_gbm_store.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_${tag}_mlmc.csv python bench.py --workload mlmc --steps 2 --warmup 1 --no-cpu-baseline > $out/launches_${tag}_mlmc.log 2>&1
 prof() { # workload kernel-regex paths
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$2" -s 1 -c 1 -o $out/prof_${tag}_$1 -f python bench.py --workload $1 --paths $3 --steps 1 --warmup 1 --no-cpu-baseline > $out/ncu_${tag}_$1.log 2>&1
