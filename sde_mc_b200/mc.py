@@ -17,7 +17,7 @@ from . import _lib as L
 from . import _spec
 from .helpers import ceil_mult, mc_estimates, partition, sample_cov
 from .nets import AdaptedPathData, Mlp, NormalJumpsPathData, NormalPathData
-from .options import ConstantShortRate
+from .options import ConstantShortRate, EuroCall
 from .varred import (EarlyStopping, apply_adapted_control_variates, apply_diffusion_control_variate,
                      fused_cv_supported, mc_cv_fused, train_adapted_control_variates,
                      train_diffusion_control_variate)
@@ -80,37 +80,43 @@ def mc_simple(num_trials, sde_solver, payoff, discounter=None, bs=None, return_n
 
 def _mc_simple_python_payoff(num_trials, sde_solver, payoff, discounter, bs, payoff_time, start):
     """mc_simple for a USER-DEFINED Option subclass (any callable on (bs, dim) tensors, options.py:156-176): the fused
-    kernels cannot evaluate Python code, so trajectories come from the path-storing kernel in batches and the payoff
-    is applied with PyTorch on the GPU, exactly as the reference does (mc.py:84-93); sums are accumulated in fp64."""
+    kernels cannot evaluate Python code, so the payoff is applied with PyTorch on the GPU as the reference does
+    (mc.py:84-93) and the sums are accumulated in fp64.
+      one shot (bs falsy): trajectories from the path-storing kernel, returned in the statistics;
+      batched            : nothing but the state the payoff reads is needed, so each batch runs the fused moments
+                           kernel with its per-path hook (`sdemc_mc_moments(per_path=...)`: 4 dim bytes per path
+                           instead of a stored trajectory), sharded over the ranks like every other estimator."""
     df = discounter(sde_solver.time_interval)
     jumps = bool(sde_solver.has_jumps)
-
-    def batch(n):
-        if jumps:
-            out, aux = sde_solver.solve(bs=n, low_storage=bool(bs))
-            idx = aux[3] if (payoff_time == 'adapted' and aux[3] is not None) else sde_solver.num_steps
-            if bs:   # low storage: only `paths` exists; its last column is the adapted index
-                idx = out.shape[1] - 1 if payoff_time == 'adapted' else sde_solver.num_steps
-        else:
-            out, aux = sde_solver.solve(bs=n)
-            idx = sde_solver.num_steps
-        return out, aux, payoff(out[:, idx]) * df
-
     if not bs:
-        out, aux, payoffs = batch(num_trials)
+        if jumps:
+            out, aux = sde_solver.solve(bs=num_trials)
+            idx = aux[3] if (payoff_time == 'adapted' and aux[3] is not None) else sde_solver.num_steps
+        else:
+            out, aux = sde_solver.solve(bs=num_trials)
+            idx = sde_solver.num_steps
+        payoffs = payoff(out[:, idx]) * df
         mean, stderr = payoffs.mean(), payoffs.std() / np.sqrt(num_trials)
         _sync(sde_solver)
         return MCStatistics(mean, stderr, time.time() - start, num_trials, out, payoffs, aux)
-    total = total_sq = 0.0
-    remaining = num_trials
-    while remaining > 0:
-        n = int(min(bs, remaining))
-        remaining -= n
-        _, _, payoffs = batch(n)
-        p64 = payoffs.double()
-        total = total + p64.sum()
-        total_sq = total_sq + (p64 * p64).sum()
-    mean, stderr = E.mean_and_stderr(float(total), float(total_sq), num_trials)
+    dev = sde_solver._compute_device()
+    index_mode = _index_mode(payoff_time) if jumps else L.INDEX_TERMINAL
+    stand_in = EuroCall(1.0)      # the kernel's own payoff slot; its moments are not read
+    with torch.cuda.device(dev):
+        totals = torch.zeros(2, dtype=torch.float64, device=dev)
+        remaining = num_trials
+        while remaining > 0:
+            n = int(min(bs, remaining))
+            remaining -= n
+            pp = {}
+            E.run_moments(sde_solver, stand_in, discounter, n, index_mode, reduce=False, per_path=pp)
+            p64 = (payoff(sde_solver._to_user_device(pp['terminal'])) * df).double().to(dev)
+            totals[0] += p64.sum()
+            totals[1] += (p64 * p64).sum()
+        if E.world()[1] > 1:
+            E.dist.all_reduce(totals, op=E.dist.ReduceOp.SUM)
+        total, total_sq = totals.tolist()
+    mean, stderr = E.mean_and_stderr(total, total_sq, num_trials)
     return MCStatistics(mean, stderr, time.time() - start, num_trials)
 
 

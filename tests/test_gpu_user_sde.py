@@ -157,8 +157,9 @@ def test_user_sde_unsupported_paths_fail_loudly():
 
 
 def test_user_defined_option_runs_on_stored_paths():
-    """a user Option subclass without kernel coefficients: trajectories from the storing kernel, payoff in PyTorch on
-    the GPU (the reference's own evaluation, mc.py:84-93) -- one-shot and batched, diffusion and jump solvers"""
+    """a user Option subclass without kernel coefficients: payoff in PyTorch on the GPU (the reference's own
+    evaluation, mc.py:84-93) -- one-shot on trajectories from the storing kernel, batched on the states the fused
+    moments kernel reports per path (no trajectory is stored); diffusion and jump solvers"""
 
     class PowerCall(sm.Option):
         def __init__(self, strike, power):
@@ -173,9 +174,18 @@ def test_user_defined_option_runs_on_stored_paths():
     one = sm.mc_simple(200000, sm.EulerSolver(gbm, 3.0, 32, device=DEV, seed=3), PowerCall(1.0, 1.0), csr)
     ref = sm.mc_simple(200000, sm.EulerSolver(gbm, 3.0, 32, device=DEV, seed=3), sm.EuroCall(1.0), csr)
     assert one.payoffs.shape == (200000,) and abs(one.sample_mean - ref.sample_mean) < 1e-6   # power 1 == EuroCall
+    # batched = the same global path ids through the fused kernel: same estimate as the one-shot call on stored paths
+    bat = sm.mc_simple(200000, sm.EulerSolver(gbm, 3.0, 32, device=DEV, seed=3), PowerCall(1.0, 1.0), csr, bs=64000)
+    assert abs(bat.sample_mean - float(one.sample_mean)) < 2e-6 and abs(bat.sample_std - float(one.sample_std)) < 2e-6
     big = sm.mc_simple(4 * 10 ** 6, sm.EulerSolver(gbm, 3.0, 32, device=DEV, seed=3), PowerCall(1.0, 1.0), csr, bs=10 ** 6)
     assert abs(big.sample_mean - sm.bs_call(1, 1, 3, 0.02, 0.3)) < 4 * big.sample_std + 1e-3
     merton = sm.Merton(0.02, 0.2, 1, -0.05, 0.3, torch.tensor([1.0]), 1)
     jm = sm.mc_simple(2 * 10 ** 6, sm.JumpEulerSolver(merton, 3.0, 50, device=DEV), PowerCall(1.0, 1.0), csr, bs=5 * 10 ** 5,
                       payoff_time='adapted')
     assert abs(jm.sample_mean - sm.merton_call(1, 1, 3, 0.02, 0.2, -0.05, 0.3, 1)) < 4 * jm.sample_std + 1e-3
+    # both payoff indices against the built-in payoff on the same seed (quirk Q1: 'terminal' = array index num_steps)
+    for ptime in ('adapted', 'terminal'):
+        mk = lambda: sm.JumpEulerSolver(merton, 3.0, 50, device=DEV, seed=9)
+        a = sm.mc_simple(300000, mk(), PowerCall(1.0, 1.0), csr, bs=10 ** 5, payoff_time=ptime)
+        b = sm.mc_simple(300000, mk(), sm.EuroCall(1.0), csr, bs=10 ** 5, payoff_time=ptime)
+        assert abs(a.sample_mean - b.sample_mean) < 2e-6, (ptime, a.sample_mean, b.sample_mean)
