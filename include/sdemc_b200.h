@@ -267,6 +267,8 @@ int sdemc_solve_paths(const sdemc_sde* sde, const sdemc_payoff* payoff /* may be
 /* H11/E4 fused: coupled fine/coarse jump-adapted (or uniform-grid) pair sharing increments and jumps,
  * accumulating D(T) (P(fine) - P(coarse)).  coarse == 0 runs the single level `fine` (mlmc.py:44-53).
  * fp32 path state (the reference's fp32 jump pair asserts, solvers.py:264: dt is clamped at 0 here instead).
+ * Uniform-grid pairs: the GEOMETRIC / ARITHMETIC families (EulerScheme) and HESTON (HestonScheme steps for both paths,
+ * DiffusionSolver.multilevel_solve solvers.py:90-119 as inherited by HestonSolver).
  * With inject != NULL and d_pair_out != NULL writes (n, 2, dim) fp32 terminal (fine, coarse) states instead. */
 int sdemc_mlmc_pair(const sdemc_sde* sde, const sdemc_payoff* payoff, int32_t fine, int32_t coarse,
                     const sdemc_range* range, const sdemc_inject* inject, sdemc_moments* d_moments,

@@ -71,7 +71,8 @@ void oracle_diffusion_pair_f32(const oracle_sde* s, int64_t n, int fine, int coa
           for (int i = 0; i < d; ++i) nz[i] = z[((p * fine + step) * d + i) * m + j] * sq;
           correlate_f32(&c, nz, w[j]);
         }
-        euler_f32(&c, xf, hf, w[0], w[1], xn);
+        if (c.heston) heston_step_f32(&c, xf, hf, w[0], xn);   /* HestonSolver: schemes.py:16-22 */
+        else euler_f32(&c, xf, hf, w[0], w[1], xn);
         for (int i = 0; i < d; ++i) {
           xf[i] = xn[i];
           paths_fine[(p * (fine + 1) + step + 1) * d + i] = xf[i];
@@ -79,7 +80,8 @@ void oracle_diffusion_pair_f32(const oracle_sde* s, int64_t n, int fine, int coa
           if (m == 2) s2[i] += w[1][i];
         }
       }
-      euler_f32(&c, xc, hc, s1, s2, xn);
+      if (c.heston) heston_step_f32(&c, xc, hc, s1, xn);
+      else euler_f32(&c, xc, hc, s1, s2, xn);
       for (int i = 0; i < d; ++i) { xc[i] = xn[i]; paths_coarse[(p * (coarse + 1) + k + 1) * d + i] = xc[i]; }
     }
   }

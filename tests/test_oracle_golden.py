@@ -29,6 +29,17 @@ def test_diffusion_pair_matches_reference():
     assert rel_err(pc, g["paths_coarse"]) < F32_RTOL
 
 
+@pytest.mark.parametrize("fine,coarse", [(8, 2), (16, 8)])
+def test_heston_pair_matches_reference(fine, coarse):
+    """HestonSolver.multilevel_solve (solvers.py:90-119 on HestonScheme steps, schemes.py:16-22), fp32"""
+    g = golden("mlmc_heston_%d_%d" % (fine, coarse))
+    sde = sm.Heston(float(g["r"]), float(g["kappa"]), float(g["theta"]), float(g["xi"]), float(g["rho"]), t(g["x0"]))
+    solver = sm.HestonSolver(sde, float(g["T"]), fine)
+    pf, pc = oracle.diffusion_pair(oracle_sde(solver, fine), fine, coarse, g["z"])
+    assert rel_err(pf, g["paths_fine"]) < 5e-6
+    assert rel_err(pc, g["paths_coarse"]) < 5e-6
+
+
 @pytest.mark.parametrize("name", sorted(JUMP_CASES))
 def test_jump_solver_matches_reference(name):
     g = golden(name)
