@@ -181,7 +181,10 @@ class DiffusionSolver(SdeSolver):
         return paths, normals
 
     def multilevel_solve(self, bs, levels, return_normals=False, inject=None):
-        """Coupled fine/coarse Euler pair on shared increments (solvers.py:90-119)."""
+        """Coupled fine/coarse pair on shared increments (solvers.py:90-119; Euler or Heston steps).
+        Returns ((paths_fine, paths_coarse), None) with paths of shape (bs, 2, dim): index 0 = the initial value,
+        index -1 = the terminal state -- what the estimators read (mlmc.py:64-65).  The reference's intermediate grid
+        points and its `corr_normals` are not materialised: the pair lives in the registers of one thread."""
         from .mlmc import _pair_paths_diffusion
         return _pair_paths_diffusion(self, int(bs), levels, inject)
 
@@ -289,7 +292,10 @@ class JumpDiffusionSolver(SdeSolver):
         return paths, aux
 
     def multilevel_solve(self, bs, levels, return_normals=False, inject=None):
-        """Coupled fine/coarse jump-adapted pair sharing increments and jumps (solvers.py:228-307)."""
+        """Coupled fine/coarse jump-adapted pair sharing increments and jumps (solvers.py:228-307).
+        Returns ((paths_fine, paths_coarse), None) with paths of shape (bs, 2, dim): index 0 = the initial value,
+        index -1 = the terminal state -- what the estimators read (mlmc.py:64-65); the reference's states at the
+        coarse iterations in between are not materialised."""
         from .mlmc import _pair_paths_jump
         return _pair_paths_jump(self, int(bs), levels, inject)
 
