@@ -24,6 +24,7 @@ struct LaunchArgs {
 
 int launch_diffusion(const sdemc_sde& s, const LaunchArgs& a);
 int launch_jump(const sdemc_sde& s, const LaunchArgs& a);
+int launch_jump_store(const sdemc_sde& s, const LaunchArgs& a);  // launch_jump's storing half (launch_jump_store.cu)
 int launch_pair(const sdemc_sde& s, const LaunchArgs& a, int fine, int coarse, float* d_terminal);
 int launch_debug_draws(const sdemc_sde& s, const DevRange& rg, const PhiloxKeys& keys, int kind, int count, float* a,
                        float* b, float* c, cudaStream_t stream);

@@ -1,4 +1,5 @@
-// launch_jump.cu -- instantiation + dispatch of the jump-adapted kernels (jump.cuh)
+// launch_jump.cu -- instantiation + dispatch of the jump-adapted MOMENTS kernels (jump.cuh, jump1d.cuh, jump_flat.cuh);
+// the path-storing kernels are instantiated in launch_jump_store.cu (a translation unit of its own: build time)
 #include <type_traits>
 
 #include <algorithm>
@@ -7,9 +8,7 @@
 #include "jump1d.cuh"
 #include "debug_draws.cuh"
 #include "jump_flat.cuh"
-#include "jump_tma.cuh"
 #include "launch.cuh"
-#include "tma_host.cuh"
 
 namespace sdemc {
 namespace {
@@ -28,63 +27,6 @@ int run(const LaunchArgs& a) {
                                            a.d_ws);
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
-}
-
-// path-storing launch through TMA (jump_tma.cuh); returns 1 when the layout does not qualify
-template <class C, int JSRC, bool FULL>
-int run_store_tma_inst(const LaunchArgs& a) {
-  const DevOut& o = a.out;
-  const uint64_t S = (uint64_t)o.S, rows = a.range.n_paths;
-  // the maps span the whole pitch (no box is cut inside a row)
-  const uint64_t len_s = tma_map_row_len((S + 1) * C::DIM, o.pitch_state);
-  const uint64_t len_t = FULL ? tma_map_row_len(S + 1, o.pitch_times) : 0;
-  const uint64_t len_n = FULL ? tma_map_row_len(S * C::DIM * C::M, o.pitch_normals) : 0;
-#ifdef SDEMC_JUMP_TMA_NO_DIRECT   // A/B builds only: the last tile always goes through TMA
-  const bool direct = false;
-#else
-  const bool direct = true;
-#endif
-  TmaRows rs = tma_rows_of((S + 1) * C::DIM, len_s, o.pitch_state, direct);
-  TmaRows rt = tma_rows_of(S + 1, len_t, o.pitch_times, direct && FULL);
-  const TmaRows rn = tma_rows_of(S * C::DIM * C::M, len_n, o.pitch_normals, direct && FULL);
-  if (FULL && C::DIM == 1) tma_rows_agree(rs, rt);  // the time rows ride in the state gang
-  CUtensorMap mp, ml, mj, mt, mn;
-  if (!make_row_map(&mp, o.paths, rows, len_s, o.pitch_state)) return 1;
-  if (FULL) {
-    if (!make_row_map(&ml, o.left, rows, len_s, o.pitch_state) || !make_row_map(&mj, o.jumps, rows, len_s, o.pitch_state) ||
-        !make_row_map(&mt, o.times, rows, len_t, o.pitch_times) || !make_row_map(&mn, o.normals, rows, len_n, o.pitch_normals))
-      return 1;
-  } else {
-    ml = mj = mt = mn = mp;
-  }
-  auto kernel = jump_store_tma_kernel<C, JSRC, FULL>;
-  const size_t smem = (JSRC == JSRC_QUEUE ? (size_t)a.qdepth * kJumpTmaBlock * sizeof(float2) : 0) + 1024 +
-                      (size_t)(kJumpTmaBlock / 32) * (FULL ? 5 : 1) * kTmaTileBytes + SDEMC_JUMP_TMA_PAD;
-  SDEMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = 0;
-  int rc = pick_grid(kernel, smem, rows, &grid, kJumpTmaBlock);
-  if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kJumpTmaBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, a.qdepth, mp, ml, mj,
-                                                   mt, mn, rs, rt, rn);
-  SDEMC_CUDA_CHECK(cudaGetLastError());
-  return SDEMC_OK;
-}
-template <class C, int JSRC>
-int run_store(const LaunchArgs& a) {
-  const DevOut& o = a.out;
-  const bool full = o.left && o.jumps && o.times && o.normals;
-  const bool low = !o.left && !o.jumps && !o.times && !o.normals;
-  bool ok = !a.no_tma && a.range.n_paths < (1ull << 31) && !a.range.dyn && (full || low) &&
-            tma_rows_ok(o.paths, o.pitch_state);
-  if (ok && full)
-    ok = tma_rows_ok(o.left, o.pitch_state) && tma_rows_ok(o.jumps, o.pitch_state) && tma_rows_ok(o.times, o.pitch_times) &&
-         tma_rows_ok(o.normals, o.pitch_normals);
-  if (ok) {
-    const int rc = full ? run_store_tma_inst<C, JSRC, true>(a) : run_store_tma_inst<C, JSRC, false>(a);
-    if (rc <= 0) return rc;
-  }
-  // any other layout (dense rows, a subset of the arrays): the 16-byte-store kernel of store_tile.cuh
-  return run<C, JSRC, true>(a);
 }
 
 // moments-only fast path for 1-D single-driver models with queued (sparse) jumps: jump1d.cuh
@@ -157,7 +99,7 @@ int by_mode(const LaunchArgs& a) {
     if (!a.use_inject && !a.store && a.qdepth > 0 && !a.sde.milstein)
       return a.sde.exact_jumps ? run_1d<C, true>(a) : run_1d<C, false>(a);
   }
-  if (a.use_inject) return a.store ? run_store<C, JSRC_INJECT>(a) : SDEMC_ERR_UNSUPPORTED;
+  if (a.use_inject) return SDEMC_ERR_UNSUPPORTED;  // injected noise is only offered with stored outputs
   if (a.short_path != SDEMC_SHORT_OFF && !a.store && a.qdepth == 0) {
     if (a.short_path == SDEMC_SHORT_ALIGNED) return run_flat<C>(a);
     // PACKED / PACKED_GENERIC: the stream of its own, 1-D lognormal-mark models only
@@ -169,8 +111,8 @@ int by_mode(const LaunchArgs& a) {
     }
     return SDEMC_ERR_UNSUPPORTED;
   }
-  if (a.qdepth > 0) return a.store ? run_store<C, JSRC_QUEUE>(a) : run<C, JSRC_QUEUE, false>(a);
-  return a.store ? run_store<C, JSRC_INLINE>(a) : run<C, JSRC_INLINE, false>(a);
+  if (a.qdepth > 0) return run<C, JSRC_QUEUE, false>(a);
+  return run<C, JSRC_INLINE, false>(a);
 }
 
 template <int FAMILY, int M, int MARKS>
@@ -201,6 +143,7 @@ int launch_debug_draws(const sdemc_sde& s, const DevRange& rg, const PhiloxKeys&
 int launch_jump(const sdemc_sde& s, const LaunchArgs& a_in) {
   LaunchArgs a = a_in;
   if (a.qdepth < 0 || (a.qdepth & 3) || a.qdepth > 64) return SDEMC_ERR_BAD_ARG;
+  if (a.store) return launch_jump_store(s, a);
   // resolve AUTO.  mc_moments keeps the Philox streams of the path-storing kernels (ALIGNED), so the batched and the
   // one-shot estimators of one seed agree; the MLMC single-level call takes the packed stream where it exists.
   if (a.short_path == SDEMC_SHORT_AUTO) {

@@ -10,7 +10,7 @@ nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC -Xptxas -v --expt-relaxed-c
      -c $root/sde_mc_b200/csrc/$tu.cu -o $obj/$tu.o 2> $obj/$tu.ptxas.log
 c=$root/sde_mc_b200/csrc
 objs=""
-for f in abi launch_diffusion launch_jump launch_pair launch_cv; do
+for f in abi launch_diffusion launch_jump launch_jump_store launch_jump_store_inject launch_jump_store_queue launch_jump_store_inline launch_pair launch_cv; do
   if [ $f = $tu ]; then objs="$objs $obj/$f.o"; else objs="$objs $c/$f.o"; fi
 done
 nvcc $ARCH -shared -o $root/variants/libsdemc_$name.so $objs -cudart static

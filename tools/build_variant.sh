@@ -6,7 +6,7 @@ name=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 obj=/tmp/sdemc_variant_$name; mkdir -p $obj $root/variants
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in abi launch_diffusion launch_jump launch_pair launch_cv; do
+for f in abi launch_diffusion launch_jump launch_jump_store launch_jump_store_inject launch_jump_store_queue launch_jump_store_inline launch_pair launch_cv; do
   nvcc -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr "$@" \
        -c $root/sde_mc_b200/csrc/$f.cu -o $obj/$f.o 2> $obj/$f.ptxas.log &
 done
