@@ -237,7 +237,9 @@ const char* sdemc_strerror(int rc);
 const char* sdemc_last_cuda_error(void);
 /* SM count, SM clock (kHz) and global memory of `device`; any pointer may be NULL. */
 int sdemc_device_info(int device, int* sm_count, int* clock_khz, uint64_t* mem_bytes);
-/* Bytes of device scratch every entry point needs (per concurrent call). */
+/* Bytes of device scratch every entry point needs (per concurrent call).  The caller zeroes it ONCE after allocation;
+ * the kernels keep a few counters in it and leave them zero when they finish.  sdemc_solve_paths accepts NULL (it then
+ * takes the LSU storing kernels: the TMA kernels hand their work out warp by warp through the workspace). */
 uint64_t sdemc_workspace_bytes(void);
 /* Layout handshake: writes up to `n` of the sizes {sdemc_sde, sdemc_payoff, sdemc_range, sdemc_inject, sdemc_moments,
  * sdemc_paths_out, sdemc_mlp, sdemc_coeffs_f64, sdemc_inject_f64} this library was compiled with and returns how many

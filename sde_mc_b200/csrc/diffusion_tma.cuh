@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kTmaStoreBlock)
     diffusion_store_tma_kernel(const DevSde s, const DevPayoff po, const DevRange rg, const PhiloxKeys keys,
                                const DevInject inj, const DevOut out, const __grid_constant__ CUtensorMap map_paths,
                                const __grid_constant__ CUtensorMap map_normals, const TmaRows rows_paths,
-                               const TmaRows rows_normals) {
+                               const TmaRows rows_normals, unsigned int* __restrict__ d_sched) {
   constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M;
   constexpr int NZ = BASE * M;                        // normals consumed per step
   constexpr int SPB = steps_per_group(NZ);            // steps served by one group of Philox blocks
@@ -79,8 +79,9 @@ __global__ void __launch_bounds__(kTmaStoreBlock)
   TmaGroups grp;
   grp.init();
 
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < rg.n_paths; wbase += stride) {
+  TmaWarpTasks tasks;  // groups of 32 consecutive paths, handed out through the caller's workspace
+  for (tasks.init(d_sched, rg.n_paths); tasks.valid(); tasks.advance()) {
+    const uint64_t wbase = tasks.first_row();
     const uint64_t i = wbase + (threadIdx.x & 31);
     const bool valid = i < rg.n_paths;
     const uint64_t gp = rg.path_lo + i;
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kTmaStoreBlock)
       for (int d = 0; d < DIM; ++d) out.terminal[i * DIM + d] = x[d];
     }
   }
+  tasks.finish();
   grp.drain();  // all bulk stores of this warp complete before the CTA retires
 }
 

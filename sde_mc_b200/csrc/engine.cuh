@@ -384,7 +384,8 @@ struct Accum {
   }
 };
 
-// workspace layout: [0, 64) bytes: uint32 ticket ; then gridDim.x * kNumMoments doubles
+// workspace layout: [0, 64) bytes: uint32 ticket of this reduction at 0, the two scheduling words of the TMA storing
+// kernels at 16 (tma_gang.cuh: WarpTasks) -- all zero between calls; then gridDim.x * kNumMoments doubles
 __device__ __forceinline__ void block_reduce_and_publish(const Accum& acc, double* d_moments, void* d_ws) {
   __shared__ double sh[32][kNumMoments];
   __shared__ bool is_last;

@@ -34,7 +34,7 @@
 // most 16 elements: 134 slots = 4 x 32 + 6 for 100 nominal steps), in which case the lanes write those columns
 // themselves as whole 32-byte sectors (tma_gang.cuh: 18 % less DRAM traffic and a fifth fewer boxes for the engine);
 // boxes wholly outside the row are not issued and rows past the end of the call are clipped by the map.
-// Merton full storage 2e6 x 100: 2.2 ms (store_tile.cuh kernel) -> 1.28 ms, 0.64 of the measured copy bandwidth;
+// Merton full storage 2e6 x 100: 2.2 ms (store_tile.cuh kernel) -> 1.24 ms, 0.66 of the measured copy bandwidth;
 // what bounds it now is in DESIGN.md section 6.
 #pragma once
 #include <cuda.h>
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
                           const __grid_constant__ CUtensorMap map_paths, const __grid_constant__ CUtensorMap map_left,
                           const __grid_constant__ CUtensorMap map_jumps, const __grid_constant__ CUtensorMap map_times,
                           const __grid_constant__ CUtensorMap map_normals, const TmaRows rows_state,
-                          const TmaRows rows_times, const TmaRows rows_normals) {
+                          const TmaRows rows_times, const TmaRows rows_normals, unsigned int* __restrict__ d_sched) {
   constexpr int DIM = C::DIM, BASE = C::BASE, M = C::M, MARKS = C::MARKS;
   constexpr int NZ = BASE + (M == 2 ? 1 : 0);  // normals per iteration
   constexpr int SPB = steps_per_group(NZ);     // iterations served by one group of Philox blocks
@@ -115,8 +115,9 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
   int local_max_iters = 0;
   const int n = s.num_steps;
   const int S = out.S;
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t wbase = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); wbase < rg.n_paths; wbase += stride) {
+  TmaWarpTasks tasks;  // groups of 32 consecutive paths, handed out through the caller's workspace
+  for (tasks.init(d_sched, rg.n_paths); tasks.valid(); tasks.advance()) {
+    const uint64_t wbase = tasks.first_row();
     const uint64_t i = wbase + (threadIdx.x & 31);
     const bool valid = i < rg.n_paths;
     const uint64_t gp = rg.path_lo + i;
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
       for (int d = 0; d < DIM; ++d) out.terminal[i * DIM + d] = xp[d];
     }
   }
+  tasks.finish();
   if (out.total_steps) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)

@@ -13,7 +13,7 @@ int run_store_tma(const LaunchArgs& a) {
   constexpr int NPS = C::BASE * C::M + (C::ASIAN ? 1 : 0);
   if (!tma_rows_ok(a.out.paths, a.out.pitch_state) || !tma_rows_ok(a.out.normals, a.out.pitch_normals)) return 1;
   if (a.range.n_paths >= (1ull << 31)) return 1;
-  if (a.no_tma) return 1;
+  if (a.no_tma || a.d_ws == nullptr) return 1;  // (the TMA kernel hands its warp tasks out through the workspace)
   CUtensorMap mp, mn;
   const uint64_t S = (uint64_t)a.sde.num_steps;
 #ifdef SDEMC_TMA_CLIP_AT_ROW_END
@@ -34,7 +34,7 @@ int run_store_tma(const LaunchArgs& a) {
   int grid = 0;
   int rc = pick_grid(kernel, smem, a.range.n_paths, &grid, kTmaStoreBlock);
   if (rc != SDEMC_OK) return rc;
-  kernel<<<grid, kTmaStoreBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, mp, mn, rp, rn);
+  kernel<<<grid, kTmaStoreBlock, smem, a.stream>>>(a.sde, a.payoff, a.range, a.keys, a.inject, a.out, mp, mn, rp, rn, tma_sched_words(a.d_ws));
   SDEMC_CUDA_CHECK(cudaGetLastError());
   return SDEMC_OK;
 }

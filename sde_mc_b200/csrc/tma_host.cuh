@@ -59,6 +59,12 @@ inline void tma_rows_agree(TmaRows& a, TmaRows& b) {
   }
 }
 
+// the two scheduling words of the storing kernels inside the caller's workspace (engine.cuh: bytes [16, 24) of the
+// 64-byte header; zero between calls).  Without a workspace the TMA kernels are not used.
+inline unsigned int* tma_sched_words(void* d_ws) {
+  return d_ws ? reinterpret_cast<unsigned int*>(static_cast<char*>(d_ws) + 16) : nullptr;
+}
+
 inline bool tma_rows_ok(const float* base, uint64_t pitch) {
   return base != nullptr && (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
 }
