@@ -91,10 +91,10 @@ PROFILE = {
                       inst=667.7, binding=None, pipe_pct=dict(issue=43.6, fma=5.6, alu=44.9, xu=6.2, tensor=41.7)),
     "mlmc": dict(source="profiles/r02_ncu_mlmc.summary.txt", capture_paths=None, dram_bytes=15616.0, inst=None,
                  binding=None, pipe_pct=dict(issue=67.6, fma=25.8, alu=54.4, xu=43.5)),
-    "gbm_store": dict(source="profiles/r02_ncu_gbm_store.summary.txt", capture_paths=4e6, dram_bytes=8.13242e9,
-                      inst=None, binding=None, pipe_pct=dict(issue=55.3, fma=20.9, alu=32.8, xu=32.6)),
-    "merton_store": dict(source="profiles/r02_ncu_merton_store.summary.txt", capture_paths=2e6, dram_bytes=5.40794e9,
-                         inst=None, binding=None, pipe_pct=dict(issue=35.7, fma=14.5, alu=20.7, xu=13.4)),
+    "gbm_store": dict(source="profiles/r02_ncu_gbm_store.summary.txt", capture_paths=4e6, dram_bytes=8.13366e9,
+                      inst=None, binding=None, pipe_pct=dict(issue=57.1, fma=20.9, alu=33.4, xu=34.6)),
+    "merton_store": dict(source="profiles/r02_ncu_merton_store.summary.txt", capture_paths=2e6, dram_bytes=5.40505e9,
+                         inst=None, binding=None, pipe_pct=dict(issue=41.0, fma=16.1, alu=25.4, xu=15.1)),
 }
 CV_TENSOR_FLOP_PER_ITER = 20000.0  # 2 nets x 2 hidden layers x 2*50*50 (unpadded)
 

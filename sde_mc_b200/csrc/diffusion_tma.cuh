@@ -101,36 +101,16 @@ __global__ void __launch_bounds__(kTmaStoreBlock)
     float t_user = 0.0f;      // fp32 clock of the grid, read by user coefficients only
     // vector v of the path rows / of the increment rows
     auto put_paths = [&](int v) {
-      if (g_paths.direct()) {
-        g_paths.begin(grp);
-        g_paths.store_tail(0, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
-        g_paths.end_tail();
-        return;
-      }
       g_paths.begin(grp);
       g_paths.store(0, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
       g_paths.end(grp);
     };
     auto put_norm = [&](int v) {
-      if (g_norm.direct()) {
-        g_norm.begin(grp);
-        g_norm.store_tail(0, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);
-        g_norm.end_tail();
-        return;
-      }
       g_norm.begin(grp);
       g_norm.store(0, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);
       g_norm.end(grp);
     };
     auto put_both = [&](int v, bool with_normals) {
-      if (g_both.direct()) {
-        g_both.begin(grp);
-        g_both.store_tail(0, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
-        if (with_normals)
-          g_both.store_tail(1, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);
-        g_both.end_tail();
-        return;
-      }
       g_both.begin(grp);
       g_both.store(0, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
       if (with_normals) g_both.store(1, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);

@@ -34,7 +34,7 @@
 // most 16 elements: 134 slots = 4 x 32 + 6 for 100 nominal steps), in which case the lanes write those columns
 // themselves as whole 32-byte sectors (tma_gang.cuh: 18 % less DRAM traffic and a fifth fewer boxes for the engine);
 // boxes wholly outside the row are not issued and rows past the end of the call are clipped by the map.
-// Merton full storage 2e6 x 100: 2.2 ms (store_tile.cuh kernel) -> 1.24 ms, 0.66 of the measured copy bandwidth;
+// Merton full storage 2e6 x 100: 2.2 ms (store_tile.cuh kernel) -> 1.11 ms, 0.74 of the measured copy bandwidth;
 // what bounds it now is in DESIGN.md section 6.
 #pragma once
 #include <cuda.h>
@@ -48,6 +48,9 @@ namespace sdemc {
 
 #ifndef SDEMC_JUMP_TMA_BLOCK
 #define SDEMC_JUMP_TMA_BLOCK 32   // threads per CTA: one warp = 20 KB of tiles (+ queue), nine CTAs per SM
+#endif
+#ifndef SDEMC_JUMP_TMA_OOL
+#define SDEMC_JUMP_TMA_OOL 1      // rare staging code (wait, flush) as out-of-line calls (tma_gang.cuh)
 #endif
 #ifndef SDEMC_JUMP_TMA_PAD
 #define SDEMC_JUMP_TMA_PAD 0      // A/B builds only: unused shared memory per CTA (lowers the residency)
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
   const uint32_t queue_bytes = JSRC == JSRC_QUEUE ? (uint32_t)qdepth * blockDim.x * (uint32_t)sizeof(float2) : 0u;
   const uint32_t warp_tiles = (((uint32_t)__cvta_generic_to_shared(jump_queue_smem) + queue_bytes + 1023u) & ~1023u) +
                               (threadIdx.x >> 5) * ((FULL ? 5u : 1u) * kTmaTileBytes);
-  TmaGang<NSTATE> g_state;
-  TmaGang<1> g_times, g_norm;
+  TmaGang<NSTATE, 1, SDEMC_JUMP_TMA_OOL != 0> g_state;
+  TmaGang<1, 1, SDEMC_JUMP_TMA_OOL != 0> g_times, g_norm;
   g_state.init(warp_tiles, rows_state.dcol);
   g_state.set_array(0, &map_paths, rows_state);
   if (FULL) {
@@ -171,19 +174,7 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
     float pb[CP + SG * DIM], lb[CP + SG * DIM], jb[CP + SG * DIM], tb[1 + SG], nb[SG * NPS];
     // vector v of the state rows / the time row / the increment row
     auto emit_state = [&](int v) {
-      if (g_state.direct()) {
-        g_state.begin(grp);
-        g_state.store_tail(0, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
-        if (FULL) {
-          g_state.store_tail(1, lb[4 * v], lb[4 * v + 1], lb[4 * v + 2], lb[4 * v + 3]);
-          g_state.store_tail(2, jb[4 * v], jb[4 * v + 1], jb[4 * v + 2], jb[4 * v + 3]);
-          if (TIMES_IN_STATE)
-            g_state.store_tail(3, tb[4 * v], tb[4 * v + 1], tb[4 * v + 2], tb[4 * v + 3]);
-        }
-        g_state.end_tail();
-        return;
-      }
-      g_state.begin(grp);
+      g_state.begin(grp);  // (first store into tiles the engine may still be reading)
       g_state.store(0, pb[4 * v], pb[4 * v + 1], pb[4 * v + 2], pb[4 * v + 3]);
       if (FULL) {
         g_state.store(1, lb[4 * v], lb[4 * v + 1], lb[4 * v + 2], lb[4 * v + 3]);
@@ -193,23 +184,11 @@ __global__ void __launch_bounds__(kJumpTmaBlock)
       g_state.end(grp);
     };
     auto emit_times = [&](int v) {
-      if (g_times.direct()) {
-        g_times.begin(grp);
-        g_times.store_tail(0, tb[4 * v], tb[4 * v + 1], tb[4 * v + 2], tb[4 * v + 3]);
-        g_times.end_tail();
-        return;
-      }
       g_times.begin(grp);
       g_times.store(0, tb[4 * v], tb[4 * v + 1], tb[4 * v + 2], tb[4 * v + 3]);
       g_times.end(grp);
     };
     auto emit_norm = [&](int v) {
-      if (g_norm.direct()) {
-        g_norm.begin(grp);
-        g_norm.store_tail(0, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);
-        g_norm.end_tail();
-        return;
-      }
       g_norm.begin(grp);
       g_norm.store(0, nb[4 * v], nb[4 * v + 1], nb[4 * v + 2], nb[4 * v + 3]);
       g_norm.end(grp);

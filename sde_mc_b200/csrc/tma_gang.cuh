@@ -38,8 +38,10 @@ constexpr int tma_lcm(int a, int b) { return a / tma_gcd(a, b) * b; }
 // with by-value arguments; a kernel picks one (template parameter OOL of the gang).  Inlined at every staging point
 // of an unrolled step loop they put ~60 cold instructions and a taken branch over them every few steps into the hot
 // path.  Measured: out of line the uniform-grid kernel gains 6 % (GBM solve() 1.54 -> 1.45 ms) and the jump kernel's
-// instruction-fetch stalls fall from 1.3 to 0.4 warps per issue cycle -- but its warps then reach the next store into
-// a tile sooner and wait longer for the engine (1.28 -> 1.41 ms), so the jump kernel keeps them inline.
+// instruction-fetch stalls fall from 1.3 to 0.3 warps per issue cycle.  (With a static partition of the paths the jump
+// kernel was slower out of line -- its phase-locked warps reached the next store into a tile sooner and waited for
+// the engine, 1.28 -> 1.41 ms; with the warp tasks handed out dynamically both forms take 1.11 ms and the smaller one
+// is kept.)
 
 // commits the open bulk group if there is one and waits until the engine has read the shared memory of every copy in
 // groups 1 .. seq; returns the number of committed groups
@@ -234,16 +236,11 @@ struct TmaGang {
   }
   // The short last tile of a row (at most 16 elements: 134 = 4 x 32 + 6 slots for 100 nominal steps) does not go
   // through the engine: a box costs it the same ~185 cycles whether 6 or 32 of its columns exist, and the kernels are
-  // bound by its box rate.  The columns are staged in the tile like any others (put_tail: no flush) and at the end of
-  // the row every lane reads its own row back and writes its last one or two 32-byte sectors with one 32-byte store
+  // bound by its box rate.  The columns are staged in the tile like any others (end() does not flush once the tile's
+  // first column has reached dcol) and at the end of the row every lane reads its own row back and writes its last one or two 32-byte sectors with one 32-byte store
   // each (write_tail).  Whole sectors, one request per sector: 16-byte stores issued as the vectors appear were
   // measured 6-20 % SLOWER than the tile (two half-sector writes per sector).  The surplus lands in the row's padding.
   __device__ __forceinline__ bool direct() const { return col >= dcol; }
-  // (in place of store + end) four elements of the tail columns of array a; columns past dend are dropped
-  __device__ __forceinline__ void store_tail(int a, float x0, float x1, float x2, float x3) {
-    if (col + (vec4 >> 2) < dend[a]) store(a, x0, x1, x2, x3);
-  }
-  __device__ __forceinline__ void end_tail() { vec4 += 16; }
   // end of the row: the staged tail columns of array a (this lane's own stores: no synchronisation needed)
   __device__ __forceinline__ void write_tail(int a, float* base, uint64_t pitch, bool row_ok) {
     float* dst = base + (uint64_t)(row0 + (int)(threadIdx.x & 31)) * pitch + col;
@@ -278,10 +275,15 @@ struct TmaGang {
     col += vec4 >> 2;       // (a partial flush only happens at the end of a row or in front of the tail columns)
     vec4 = 0;
   }
-  // after the stores of a vector
+  // after the stores of a vector.  A full tile is flushed -- unless it holds the tail columns (direct()): those wait
+  // for write_tail, and the surplus vectors a kernel stages past the end of the row (at most SG / 4 + 1, the tail has
+  // at most four) pile up in the tile's last slot.
   __device__ __forceinline__ void end(TmaGroups& g) {
     vec4 += 16;
-    if (vec4 == W * 128 || (W > 1 && col + (vec4 >> 2) == dcol)) flush(g);
+    if (vec4 == W * 128 || (W > 1 && col + (vec4 >> 2) == dcol)) {
+      if (direct()) vec4 -= 16;
+      else flush(g);
+    }
   }
   // end of the rows of this group of 32 paths (tail columns: write_tail of every array first)
   __device__ __forceinline__ void finish(TmaGroups& g) {
